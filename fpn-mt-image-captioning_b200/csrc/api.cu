@@ -1,0 +1,209 @@
+// extern "C" surface of libfpnmt.so (see include/fpnmt.h).
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace fpnmt {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace fpnmt
+
+using namespace fpnmt;
+
+struct fpnmt_handle {
+  Engine* eng;
+};
+
+extern "C" {
+
+FPNMT_API const char* fpnmt_version(void) {
+  return "fpnmt 0.1 (sm_100a; tcgen05 implicit-GEMM igemm_kernel<32|64|128|256>, TMA, TMEM; CUDA-core tail kernels)";
+}
+FPNMT_API const char* fpnmt_last_error(void) { return g_last_error.c_str(); }
+
+FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** out) {
+  if (!cfg || !out) {
+    set_last_error("fpnmt_create: NULL argument");
+    return FPNMT_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("fpnmt_create: no CUDA device (this library has no CPU fallback)");
+    return FPNMT_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_last_error("fpnmt_create: bad device index");
+    return FPNMT_ERR_INVALID;
+  }
+  Engine* e = new (std::nothrow) Engine(*cfg, device);
+  if (!e) return FPNMT_ERR_INVALID;
+  int rc = e->init();
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *out = new fpnmt_handle{e};
+  return FPNMT_OK;
+}
+
+FPNMT_API int fpnmt_destroy(fpnmt_handle* h) {
+  if (!h) return FPNMT_OK;
+  delete h->eng;
+  delete h;
+  return FPNMT_OK;
+}
+
+#define CHECK_H(h)                                 \
+  if (!(h) || !(h)->eng) {                         \
+    set_last_error("NULL handle");                 \
+    return FPNMT_ERR_INVALID;                      \
+  }
+
+FPNMT_API int fpnmt_set_weight(fpnmt_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  CHECK_H(h);
+  return h->eng->set_weight(key, data, shape, ndim);
+}
+FPNMT_API int fpnmt_finalize_weights(fpnmt_handle* h) {
+  CHECK_H(h);
+  return h->eng->finalize();
+}
+FPNMT_API int fpnmt_encode(fpnmt_handle* h, const float* images, int on_host, float* memory_out, void* stream) {
+  CHECK_H(h);
+  return h->eng->encode(images, on_host, memory_out, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_features(fpnmt_handle* h, const float* images, int on_host, float* const out5[5], void* stream) {
+  CHECK_H(h);
+  return h->eng->features(images, on_host, out5, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_get_tap(fpnmt_handle* h, const char* name, float* out, size_t capacity, size_t* count, void* stream) {
+  CHECK_H(h);
+  return h->eng->get_tap(name, out, capacity, count, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_decode_logits(fpnmt_handle* h, const float* memory, const int32_t* tokens, int t, float* logits_out,
+                        void* stream) {
+  CHECK_H(h);
+  return h->eng->decode_logits(memory, tokens, t, logits_out, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_beam_step(fpnmt_handle* h, const float* logits, const float* scores_in, int32_t* parent, int32_t* token,
+                    float* scores_out, void* stream) {
+  CHECK_H(h);
+  return h->eng->beam_step(logits, scores_in, parent, token, scores_out, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_generate(fpnmt_handle* h, const float* images, int on_host, int32_t* out_ids, int32_t* out_len,
+                   int outputs_on_host, int early_stop, float* step_scores, void* stream) {
+  CHECK_H(h);
+  return h->eng->generate(images, on_host, out_ids, out_len, outputs_on_host, early_stop, step_scores,
+                          (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_decode(fpnmt_handle* h, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop,
+                 float* step_scores, void* stream) {
+  CHECK_H(h);
+  return h->eng->decode(out_ids, out_len, outputs_on_host, early_stop, step_scores, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_profile(fpnmt_handle* h, int iters, char* buf, size_t cap) {
+  CHECK_H(h);
+  return h->eng->profile(iters, buf, cap);
+}
+FPNMT_API int64_t fpnmt_launch_count(fpnmt_handle* h) {
+  if (!h || !h->eng) return 0;
+  return h->eng->launches;
+}
+
+// ---- stand-alone convolution operator -----------------------------------------------------------------
+static inline uint16_t f2bf_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f_host(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, int H, int W, int Cin, const float* kernel, int kh,
+                    int kw, int Cout, int pad_top, int pad_left, const float* bias, int act, const float* residual,
+                    int res_mode, float* out, int force_bn, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cin % 8) {
+    set_last_error("op_conv2d: Cin must be a multiple of 8");
+    return FPNMT_ERR_INVALID;
+  }
+  FPNMT_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FPNMT_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("op_conv2d: device is not sm_100");
+    return FPNMT_ERR_CUDA;
+  }
+  int rc = igemm_set_attributes();
+  if (rc) return rc;
+  const bool split = precision == FPNMT_PREC_BF16X3;
+  const int K = kh * kw * Cin;
+  const size_t ldw = split ? 2 * (size_t)K : (size_t)K;
+  std::vector<uint16_t> hw((size_t)Cout * ldw);
+  for (int t = 0; t < kh * kw; ++t)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int o = 0; o < Cout; ++o) {
+        const float f = kernel[((size_t)t * Cin + ci) * Cout + o];
+        const uint16_t hi = f2bf_host(f);
+        hw[(size_t)o * ldw + (size_t)t * Cin + ci] = hi;
+        if (split) hw[(size_t)o * ldw + K + (size_t)t * Cin + ci] = f2bf_host(f - bf2f_host(hi));
+      }
+  std::vector<void*> tmp;
+  auto dal = [&](size_t b) {
+    void* p = nullptr;
+    cudaMalloc(&p, b ? b : 16);
+    tmp.push_back(p);
+    return p;
+  };
+  auto cleanup = [&]() {
+    for (void* p : tmp) cudaFree(p);
+  };
+  bf16* dw = (bf16*)dal(hw.size() * 2);
+  float* dbias = nullptr;
+  if (bias) {
+    dbias = (float*)dal((size_t)(Cout + 8) * 4);
+    cudaMemcpyAsync(dbias, bias, (size_t)Cout * 4, cudaMemcpyHostToDevice, s);
+  }
+  cudaMemcpyAsync(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice, s);
+  auto mk = [&](size_t pix, int C) {
+    Act a;
+    const int cs = C < 8 ? 8 : (C + 7) / 8 * 8;
+    a.C = C;
+    a.ld = split ? 2 * cs : cs;
+    a.lo = split ? cs : 0;
+    a.p = (bf16*)dal(pix * a.ld * 2);
+    return a;
+  };
+  const size_t pix = (size_t)N * H * W;
+  Act ax = mk(pix, Cin), ao = mk(pix, Cout), ar{nullptr, 0, 0, 0};
+  rc = launch_f32_to_act(x, pix, Cin, ax, s);
+  if (!rc && residual) {
+    const size_t rpix = res_mode == RES_UP2 ? (size_t)N * (H / 2) * (W / 2) : pix;
+    ar = mk(rpix, Cout);
+    rc = launch_f32_to_act(residual, rpix, Cout, ar, s);
+  }
+  IgemmOp op;
+  ConvGeom g{N, H, W, Cin, Cout, kh, kw, pad_top, pad_left};
+  if (!rc)
+    rc = make_igemm_op(&op, g, ax, dw, split, dbias, act, ao, nullptr, 0, residual ? res_mode : RES_NONE, ar,
+                       prop.multiProcessorCount, force_bn);
+  if (!rc) rc = igemm_launch(op, s);
+  if (!rc) rc = launch_act_to_f32(ao, pix, out, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cleanup();
+  if (!rc && e != cudaSuccess) {
+    set_last_error(std::string("op_conv2d: ") + cudaGetErrorString(e));
+    return FPNMT_ERR_CUDA;
+  }
+  return rc;
+}
+
+}  // extern "C"

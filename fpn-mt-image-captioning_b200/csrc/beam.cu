@@ -1,0 +1,307 @@
+// Decode tail of one beam-search step (reference: /root/reference/utils/pipeline.py:115-148).
+//   phase 1  k_beam_rowtopk : per (image, beam) row of fp32 logits: max, sum-exp, candidate score
+//                             (prob mode: softmax * beam_prob; log mode: log_softmax + beam_logprob),
+//                             row-local top-N with tf.math.top_k tie order (lower index first).
+//                             128-bit loads, values kept in registers, warp-shuffle + smem reductions.
+//   phase 2  k_beam_merge   : per image merge N x N candidates (ties -> lower flat index n*V+v), emit
+//                             parent/token/score, reorder token sequences and the KV-cache ancestry table by
+//                             parent, handle <end> on the top beam, advance the device step counter.
+//   k_kv_gather             : physical KV-cache reorder by parent (the bandwidth-bound alternative to the
+//                             ancestry table; used by the "physical" cache mode).
+#include "kernels.cuh"
+
+namespace fpnmt {
+
+#define LAUNCH_CHECK() FPNMT_CUDA_OK(cudaGetLastError())
+
+constexpr int RT_MAXV4 = 12;   // float4 loads per thread -> V <= 48 * blockDim
+
+__global__ void k_beam_init(BeamState st, int true_beam) {
+  const int rows = st.B * st.N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    *st.step = 0;
+    *st.n_done = 0;
+    st.n_done[1] = 0;   // block-completion counter used by k_beam_merge
+  }
+  if (i < st.B) {
+    st.done[i] = 0;
+    st.out_len[i] = 0;
+  }
+  if (i < rows) {
+    const int n = i % st.N;
+    float s0 = st.prob_mode ? 1.f : 0.f;
+    if (true_beam && n > 0) s0 = st.prob_mode ? 0.f : -INFINITY;
+    st.score[0][i] = s0;
+    st.seq[0][(size_t)i * (st.T + 1)] = st.start_id;
+    st.last_tok[i] = st.start_id;
+  }
+  for (size_t j = i; j < (size_t)st.B * st.T; j += (size_t)gridDim.x * blockDim.x) st.out_ids[j] = 0;
+}
+int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s) {
+  const int rows = st.B * st.N;
+  k_beam_init<<<(rows + 255) / 256, 256, 0, s>>>(st, true_beam);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// (value, index) arg-max with tf.math.top_k ordering: larger value first, equal values -> lower index
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better(ov, oi, v, i)) {
+      v = ov;
+      i = oi;
+    }
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const float* __restrict__ logits, int ld) {
+  __shared__ float s_f[32];
+  __shared__ int s_i[32];
+  __shared__ float s_bc;
+  __shared__ int s_bi;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int V = st.V, N = st.N;
+  const int t = *st.step;
+  const float score = st.score[t & 1][row];
+  const float* x = logits + (size_t)row * ld;
+
+  float v[RT_MAXV4 * 4];
+#pragma unroll
+  for (int i = 0; i < RT_MAXV4; ++i) {
+    const int e = (i * blockDim.x + tid) * 4;
+    if (e + 3 < V) {
+      const float4 q = *reinterpret_cast<const float4*>(x + e);
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * i + j] = (e + j < V) ? x[e + j] : -INFINITY;
+    }
+  }
+  // row max
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < RT_MAXV4 * 4; ++i) m = fmaxf(m, v[i]);
+  m = warp_max(m);
+  if (lane == 0) s_f[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float q = lane < nw ? s_f[lane] : -INFINITY;
+    q = warp_max(q);
+    if (lane == 0) s_bc = q;
+  }
+  __syncthreads();
+  m = s_bc;
+  // sum exp
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < RT_MAXV4 * 4; ++i) sum += expf(v[i] - m);   // exp(-inf) = 0 for the padding
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) s_f[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float q = lane < nw ? s_f[lane] : 0.f;
+    q = warp_sum(q);
+    if (lane == 0) s_bc = q;
+  }
+  __syncthreads();
+  sum = s_bc;
+  // candidate scores
+  if (st.prob_mode) {
+#pragma unroll
+    for (int i = 0; i < RT_MAXV4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i * blockDim.x + tid) * 4 + j;
+        v[4 * i + j] = (e < V) ? (expf(v[4 * i + j] - m) / sum) * score : -INFINITY;   // pipeline.py:117,122
+      }
+  } else {
+    const float lse = m + logf(sum);
+#pragma unroll
+    for (int i = 0; i < RT_MAXV4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i * blockDim.x + tid) * 4 + j;
+        v[4 * i + j] = (e < V) ? score + (v[4 * i + j] - lse) : -INFINITY;
+      }
+  }
+  // N rounds of block-wide arg-max with exclusion
+  unsigned long long taken = 0ull;
+  for (int k = 0; k < N; ++k) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < RT_MAXV4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i * blockDim.x + tid) * 4 + j;
+        const bool free_slot = !((taken >> (4 * i + j)) & 1ull) && e < V;
+        if (free_slot && better(v[4 * i + j], e, bv, bi)) {
+          bv = v[4 * i + j];
+          bi = e;
+        }
+      }
+    warp_argmax(bv, bi);
+    __syncthreads();
+    if (lane == 0) {
+      s_f[warp] = bv;
+      s_i[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float qv = lane < nw ? s_f[lane] : -INFINITY;
+      int qi = lane < nw ? s_i[lane] : 0x7fffffff;
+      warp_argmax(qv, qi);
+      if (lane == 0) {
+        s_bc = qv;
+        s_bi = qi;
+        st.cand_val[(size_t)row * N + k] = qv;
+        st.cand_idx[(size_t)row * N + k] = qi;
+      }
+    }
+    __syncthreads();
+    const int win = s_bi;
+    if (win != 0x7fffffff) {
+      const int slot4 = win >> 2;                       // which float4 of the row
+      if (slot4 % (int)blockDim.x == tid) taken |= 1ull << (4 * (slot4 / (int)blockDim.x) + (win & 3));
+    }
+  }
+}
+int launch_beam_rowtopk(const BeamState& st, const float* logits, int ld, cudaStream_t s) {
+  if (512 * RT_MAXV4 * 4 < st.V) {
+    set_last_error("beam_rowtopk: vocabulary too large (max 24576)");
+    return 1;
+  }
+  if (st.N > 32 || (ld & 3)) {
+    set_last_error("beam_rowtopk: beam width must be <= 32 and logits ld a multiple of 4");
+    return 1;
+  }
+  if (256 * RT_MAXV4 * 4 >= st.V)
+    k_beam_rowtopk<256><<<st.B * st.N, 256, 0, s>>>(st, logits, ld);
+  else
+    k_beam_rowtopk<512><<<st.B * st.N, 512, 0, s>>>(st, logits, ld);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// one warp per image
+__global__ void __launch_bounds__(32) k_beam_merge(BeamState st) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int N = st.N, V = st.V, T = st.T;
+  const int t = *st.step;
+  const int cur = t & 1, nxt = cur ^ 1;
+  const int NN = N * N;
+  // each lane holds candidates lane, lane+32, ...  (N <= 32 -> at most 32 per lane)
+  unsigned taken = 0u;
+  int my_parent = 0, my_token = 0;
+  float my_score = 0.f;
+  for (int k = 0; k < N; ++k) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    int bslot = -1;
+    for (int c = lane, s = 0; c < NN; c += 32, ++s) {
+      if ((taken >> s) & 1u) continue;
+      const int n = c / N;
+      const float val = st.cand_val[(size_t)(b * N) * N + c];
+      const int tok = st.cand_idx[(size_t)(b * N) * N + c];
+      if (tok == 0x7fffffff) continue;
+      const int flat = n * V + tok;
+      if (bslot < 0 || better(val, flat, bv, bi)) {
+        bv = val;
+        bi = flat;
+        bslot = s;
+      }
+    }
+    float wv = bv;
+    int wi = bi;
+    warp_argmax(wv, wi);
+    if (bslot >= 0 && wi == bi && wv == bv) taken |= 1u << bslot;    // flat indices are unique -> one owner
+    if (lane == k) {
+      my_parent = wi / V;                                            // pipeline.py:130
+      my_token = wi - my_parent * V;                                 // pipeline.py:131
+      my_score = wv;
+    }
+  }
+  // lanes 0..N-1 now hold the new beams in rank order
+  const int rows0 = b * N;
+  if (lane < N) {
+    st.score[nxt][rows0 + lane] = my_score;
+    st.last_tok[rows0 + lane] = my_token;
+    if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + lane] = my_parent;
+    if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + lane] = my_token;
+  }
+  if (lane == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = my_score;
+  for (int n = 0; n < N; ++n) {
+    const int par = __shfl_sync(0xffffffffu, my_parent, n);
+    const int tok = __shfl_sync(0xffffffffu, my_token, n);
+    const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
+    int* dseq = st.seq[nxt] + (size_t)(rows0 + n) * (T + 1);
+    for (int j = lane; j <= t; j += 32) dseq[j] = sseq[j];            // pipeline.py:134-137
+    const int* sanc = st.anc[cur] + (size_t)(rows0 + par) * T;
+    int* danc = st.anc[nxt] + (size_t)(rows0 + n) * T;
+    for (int j = lane; j < t; j += 32) danc[j] = sanc[j];
+    if (lane == 0) {
+      dseq[t + 1] = tok;
+      danc[t] = rows0 + par;
+    }
+  }
+  __syncwarp();
+  // top beam is rank 0 (scores are sorted; tf.argmax returns the first maximum) — pipeline.py:143-148
+  const int top_tok = __shfl_sync(0xffffffffu, my_token, 0);
+  if (!st.done[b] && (top_tok == st.end_id || t == T - 1)) {
+    const int* res = st.seq[nxt] + (size_t)rows0 * (T + 1);
+    const int len = (top_tok == st.end_id) ? t : t + 1;               // strip <start> and a trailing <end>
+    for (int j = lane; j < len; j += 32) st.out_ids[(size_t)b * T + j] = res[1 + j];
+    __syncwarp();
+    if (lane == 0) {
+      st.out_len[b] = len;
+      st.done[b] = 1;
+      atomicAdd(st.n_done, 1);
+    }
+  }
+  // last block to finish advances the step counter
+  if (lane == 0) {
+    __threadfence();
+    const int prev = atomicAdd(st.n_done + 1, 1);
+    if (prev == st.B - 1) {
+      st.n_done[1] = 0;
+      *st.step = t + 1;
+    }
+  }
+}
+int launch_beam_merge(const BeamState& st, cudaStream_t s) {
+  k_beam_merge<<<st.B, 32, 0, s>>>(st);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[row][0..step][:] = src[src_row[row]][0..step][:]   (16-byte vectors; grid-stride)
+__global__ void k_kv_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ src_row,
+                            int rows, int T, int row_vec, const int* __restrict__ step) {
+  const int t = *step;   // positions 0..t are live
+  const size_t per_row = (size_t)(t + 1) * row_vec;
+  const size_t total = (size_t)rows * per_row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / per_row);
+    const size_t off = i % per_row;
+    dst[(size_t)r * T * row_vec + off] = src[(size_t)src_row[r] * T * row_vec + off];
+  }
+}
+int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
+                     cudaStream_t s) {
+  const int row_vec = row_elems / 8;
+  k_kv_gather<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), src_row, rows,
+                                      T, row_vec, step);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fpnmt

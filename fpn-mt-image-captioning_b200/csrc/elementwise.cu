@@ -1,0 +1,389 @@
+// Bandwidth-bound NHWC kernels: 128-bit loads/stores over 8 channels per thread, grids sized to the data.
+#include "kernels.cuh"
+
+namespace fpnmt {
+
+static inline int nblocks(size_t work, int threads) { return (int)((work + threads - 1) / threads); }
+#define LAUNCH_CHECK() FPNMT_CUDA_OK(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------- im2col (stem)
+__global__ void k_im2col_stem(const float* const* __restrict__ img_slot, int N, int H, int W, int kh, int kw, int stride, int pad_t,
+                              int pad_l, int Ho, int Wo, Act out) {
+  const float* __restrict__ img = *img_slot;
+  const int groups = out.C / 8;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  const int ktot = kh * kw * 3;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = g * 8 + i;
+    float val = 0.f;
+    if (k < ktot) {
+      const int c = k % 3;
+      const int kx = (k / 3) % kw;
+      const int ky = k / (3 * kw);
+      const int y = yo * stride + ky - pad_t;
+      const int x = xo * stride + kx - pad_l;
+      if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(img + (((size_t)n * H + y) * W + x) * 3 + c);
+    }
+    v[i] = val;
+  }
+  st_act8(out, pix, g * 8, v);
+}
+int launch_im2col_stem(const float* const* img, int N, int H, int W, int kh, int kw, int stride, int pad_t, int pad_l, int Ho,
+                       int Wo, Act out, cudaStream_t s) {
+  const size_t total = (size_t)N * Ho * Wo * (out.C / 8);
+  k_im2col_stem<<<nblocks(total, 256), 256, 0, s>>>(img, N, H, W, kh, kw, stride, pad_t, pad_l, Ho, Wo, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- pooling
+__global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                          int zero_pad, Act out) {
+  const int groups = in.C / 8;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int ky = 0; ky < k; ++ky) {
+    const int y = yo * stride + ky - pad_t;
+    for (int kx = 0; kx < k; ++kx) {
+      const int x = xo * stride + kx - pad_l;
+      if (y < 0 || y >= H || x < 0 || x >= W) {
+        if (zero_pad) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+        }
+        continue;
+      }
+      float v[8];
+      ld_act8(in, ((size_t)n * H + y) * W + x, g * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+    }
+  }
+  st_act8(out, pix, g * 8, m);
+}
+int launch_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, bool zero_pad,
+                   Act out, cudaStream_t s) {
+  const size_t total = (size_t)N * Ho * Wo * (in.C / 8);
+  k_maxpool<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_avgpool2(Act in, int N, int H, int W, Act out) {
+  const int groups = in.C / 8;
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      float v[8];
+      ld_act8(in, ((size_t)n * H + 2 * yo + dy) * W + 2 * xo + dx, g * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += v[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] *= 0.25f;
+  st_act8(out, pix, g * 8, a);
+}
+int launch_avgpool2(Act in, int N, int H, int W, Act out, cudaStream_t s) {
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (in.C / 8);
+  k_avgpool2<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_subsample2(Act in, int N, int H, int W, Act out) {
+  const int groups = in.C / 8;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  const size_t ipix = ((size_t)n * H + 2 * yo) * W + 2 * xo;
+  const bf16* src = in.p + ipix * (size_t)in.ld + g * 8;
+  bf16* dst = out.p + pix * (size_t)out.ld + g * 8;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);           // exact copy of hi
+  if (in.lo) *reinterpret_cast<uint4*>(dst + out.lo) = *reinterpret_cast<const uint4*>(src + in.lo);   // and lo
+}
+int launch_subsample2(Act in, int N, int H, int W, Act out, cudaStream_t s) {
+  const size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (in.C / 8);
+  k_subsample2<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- depthwise 3x3
+__global__ void k_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                               const float* __restrict__ w, const float* __restrict__ bias, int act, Act out) {
+  const int C = in.C;
+  const int groups = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = bias ? bias[g * 8 + i] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y = yo * stride + ky - pad_t;
+    if (y < 0 || y >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int x = xo * stride + kx - pad_l;
+      if (x < 0 || x >= W) continue;
+      float v[8];
+      ld_act8(in, ((size_t)n * H + y) * W + x, g * 8, v);
+      const float4 w0 = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + g * 8 + 4);
+      a[0] = fmaf(v[0], w0.x, a[0]); a[1] = fmaf(v[1], w0.y, a[1]); a[2] = fmaf(v[2], w0.z, a[2]); a[3] = fmaf(v[3], w0.w, a[3]);
+      a[4] = fmaf(v[4], w1.x, a[4]); a[5] = fmaf(v[5], w1.y, a[5]); a[6] = fmaf(v[6], w1.z, a[6]); a[7] = fmaf(v[7], w1.w, a[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = apply_act(a[i], act);
+  st_act8(out, pix, g * 8, a);
+}
+int launch_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int pad_l, int Ho, int Wo, const float* w,
+                        const float* bias, int act, Act out, cudaStream_t s) {
+  const size_t total = (size_t)N * Ho * Wo * (in.C / 8);
+  k_depthwise3x3<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, stride, pad_t, pad_l, Ho, Wo, w, bias, act, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- BN+ReLU (pre-activation)
+__global__ void k_scale_shift_relu(Act in, size_t pixels, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, Act out) {
+  const int groups = in.C / 8;
+  const size_t total = pixels * groups;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const size_t pix = idx / groups;
+  float v[8];
+  ld_act8(in, pix, g * 8, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(v[i], scale[g * 8 + i], shift[g * 8 + i]), 0.f);
+  st_act8(out, pix, g * 8, v);
+}
+int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const float* shift, Act out, cudaStream_t s) {
+  const size_t total = pixels * (in.C / 8);
+  k_scale_shift_relu<<<nblocks(total, 256), 256, 0, s>>>(in, pixels, scale, shift, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- co-attention
+// grid (chunks, N); each block recomputes the image's softmax statistics (HW <= 4096 scores, L2 resident)
+// and scales `pix_per_block` pixels x C channels.
+__global__ void k_coattention(Act score, Act cls, int HW, int pix_per_block, Act out) {
+  __shared__ float red[32];
+  __shared__ float s_max, s_inv;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int p = tid; p < HW; p += blockDim.x) m = fmaxf(m, ld_act(score, (size_t)n * HW + p, 0));
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) s_max = t;
+  }
+  __syncthreads();
+  m = s_max;
+  float sum = 0.f;
+  for (int p = tid; p < HW; p += blockDim.x) sum += __expf(ld_act(score, (size_t)n * HW + p, 0) - m);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) s_inv = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  const int groups = cls.C / 8;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int work = pix_per_block * groups;
+  for (int i = tid; i < work; i += blockDim.x) {
+    const int p = p0 + i / groups;
+    if (p >= HW) break;
+    const int g = i % groups;
+    const size_t pix = (size_t)n * HW + p;
+    const float wgt = __expf(ld_act(score, pix, 0) - m) * inv;
+    float v[8];
+    ld_act8(cls, pix, g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= wgt;
+    st_act8(out, pix, g * 8, v);
+  }
+}
+int launch_coattention(Act score, Act cls, int N, int HW, Act out, cudaStream_t s) {
+  const int ppb = 32;
+  dim3 grid((HW + ppb - 1) / ppb, N);
+  k_coattention<<<grid, 256, 0, s>>>(score, cls, HW, ppb, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm family
+// one warp per row of C = 512 (16 values per lane, two-pass statistics in registers)
+template <typename LoadFn>
+__device__ __forceinline__ void ln_row_512(LoadFn load, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           float eps, const float* __restrict__ add, const Act& out, size_t orow,
+                                           int lane) {
+  float v[16];
+  load(lane * 8, v);
+  load(256 + lane * 8, v + 8);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / 512.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 512.f) + eps);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 256 + lane * 8;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = (v[h * 8 + i] - mean) * rstd * gamma[c + i] + beta[c + i];
+      if (add) o[i] += add[c + i];
+    }
+    st_act8(out, orow, c, o);
+  }
+}
+
+__global__ void k_tokens_ln_pos(Act in, int HW, size_t rows, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, const float* __restrict__ pos, Act out) {
+  const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int p = (int)(row % HW);
+  ln_row_512([&](int c, float* f) { ld_act8(in, row, c, f); }, gamma, beta, eps, pos + (size_t)p * 512, out, row, lane);
+}
+int launch_tokens_ln_pos(Act in, int N, int HW, const float* gamma, const float* beta, float eps, const float* pos,
+                         Act out, cudaStream_t s) {
+  if (in.C != 512) {
+    set_last_error("tokens_ln_pos: d_model must be 512");
+    return 1;
+  }
+  const size_t rows = (size_t)N * HW;
+  k_tokens_ln_pos<<<nblocks(rows, 8), 256, 0, s>>>(in, HW, rows, gamma, beta, eps, pos, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_layernorm_rows(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, Act out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)row * 512;
+  ln_row_512(
+      [&](int c, float* f) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + c);
+        const float4 b = *reinterpret_cast<const float4*>(xr + c + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      },
+      gamma, beta, eps, nullptr, out, (size_t)row, lane);
+}
+int launch_layernorm_rows(const float* x, int rows, int C, const float* gamma, const float* beta, float eps, Act out,
+                          cudaStream_t s) {
+  if (C != 512) {
+    set_last_error("layernorm_rows: d_model must be 512");
+    return 1;
+  }
+  k_layernorm_rows<<<nblocks(rows, 8), 256, 0, s>>>(x, rows, gamma, beta, eps, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- embedding + position
+__global__ void k_embed_pos(const int* __restrict__ tokens, const float* __restrict__ emb, const float* __restrict__ pos,
+                            const int* __restrict__ step, int rows, int C, Act out) {
+  const int groups = C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const int g = idx % groups, r = idx / groups;
+  const int t = *step;
+  const float* e = emb + (size_t)tokens[r] * C + g * 8;
+  const float* p = pos + (size_t)t * C + g * 8;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = e[i] + p[i];
+  st_act8(out, (size_t)r, g * 8, v);
+}
+int launch_embed_pos(const int* tokens, const float* emb, const float* pos, const int* step, int rows, int C, Act out,
+                     cudaStream_t s) {
+  k_embed_pos<<<nblocks((size_t)rows * (C / 8), 256), 256, 0, s>>>(tokens, emb, pos, step, rows, C, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- conversions
+__global__ void k_f32_to_act(const float* __restrict__ x, size_t rows, int C, Act out) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  st_act(out, idx / C, (int)(idx % C), x[idx]);
+}
+int launch_f32_to_act(const float* x, size_t rows, int C, Act out, cudaStream_t s) {
+  k_f32_to_act<<<nblocks(rows * C, 256), 256, 0, s>>>(x, rows, C, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+__global__ void k_act_to_f32(Act in, size_t rows, float* __restrict__ out) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * in.C) return;
+  out[idx] = ld_act(in, idx / in.C, (int)(idx % in.C));
+}
+int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s) {
+  k_act_to_f32<<<nblocks(rows * in.C, 256), 256, 0, s>>>(in, rows, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fpnmt

@@ -1,0 +1,1103 @@
+// Engine implementation: weight preparation (BN folding, projection fusion, bf16 / split-bf16 conversion),
+// program construction for the three backbones + FPN + heads + Multi-Transformer encoder + KV-cached decoder,
+// and execution (eager or CUDA-graph replay).
+//
+// Reference behaviour followed (paths relative to the reference repo):
+//   backbones            models/mobilenet.py:55-72, models/resnet.py:97-112, models/densenet.py:89-103 (+ SURVEY App. C)
+//   FPN                  models/retinanet.py:105-141
+//   head sub-model       models/retinanet.py:25-102, 283-301 ; models/coattention.py:13-32
+//   encoder pre-amble    models/transformer.py:279-296 ; encoder layers :176-200, :298-299
+//   decoder              models/transformer.py:224-243, :321-341, :359-374
+//   beam loop            utils/pipeline.py:82-154
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace fpnmt {
+
+static const char* TR = "transformer";
+static const std::string RN = "transformer/encoder/feature_extractor/retinanet_model";
+static const std::string HM = "transformer/encoder/feature_extractor/model";
+
+#define RC(expr)            \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+static int fail(int code, const std::string& msg) {
+  set_last_error(msg);
+  return code;
+}
+
+// --------------------------------------------------------------------------------------------- basics
+Engine::Engine(const fpnmt_config& cfg, int device) : cfg_(cfg), dev_(device) { split_ = cfg.precision == FPNMT_PREC_BF16X3; }
+
+Engine::~Engine() {
+  cudaSetDevice(dev_);
+  if (cnn_graph_) cudaGraphExecDestroy(cnn_graph_);
+  if (enc_graph_) cudaGraphExecDestroy(enc_graph_);
+  if (step_graph_) cudaGraphExecDestroy(step_graph_);
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  if (h_pinned_) cudaFreeHost(h_pinned_);
+  for (void* p : allocs_) cudaFree(p);
+}
+
+int Engine::init() {
+  const fpnmt_config& c = cfg_;
+  if (c.d_model != 512 || c.num_heads != 8) return fail(FPNMT_ERR_INVALID, "d_model must be 512 and num_heads 8");
+  if (c.batch < 1 || c.beam < 1 || c.beam > 32 || c.vocab < 8 || c.max_len < 1 || c.num_layers < 1)
+    return fail(FPNMT_ERR_INVALID, "bad batch / beam / vocab / max_len / num_layers");
+  if (c.vocab % 8) return fail(FPNMT_ERR_INVALID, "vocab must be a multiple of 8");
+  if (c.image_size < 256 || c.image_size % 256) return fail(FPNMT_ERR_INVALID, "image_size must be a multiple of 256");
+  if (c.dff % 8) return fail(FPNMT_ERR_INVALID, "dff must be a multiple of 8");
+  if (c.backbone < 0 || c.backbone > 2) return fail(FPNMT_ERR_INVALID, "unknown backbone");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  cudaDeviceProp prop;
+  FPNMT_CUDA_OK(cudaGetDeviceProperties(&prop, dev_));
+  if (prop.major != 10) return fail(FPNMT_ERR_CUDA, "this library contains sm_100a code only; device is not Blackwell");
+  num_sms_ = prop.multiProcessorCount;
+  RC(igemm_set_attributes());
+  FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+  FPNMT_CUDA_OK(cudaMallocHost(&h_pinned_, 64));
+  return 0;
+}
+
+void* Engine::dalloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_last_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed (engine holds " + std::to_string(alloc_bytes_) + ")");
+    return nullptr;
+  }
+  allocs_.push_back(p);
+  alloc_bytes_ += bytes;
+  return p;
+}
+
+Tensor Engine::new_act(int N, int H, int W, int C) {
+  Tensor t;
+  t.N = N; t.H = H; t.W = W;
+  const int cs = std::max(8, (C + 7) / 8 * 8);
+  t.a.C = C;
+  t.a.ld = split_ ? 2 * cs : cs;
+  t.a.lo = split_ ? cs : 0;
+  t.a.p = (bf16*)dalloc((size_t)N * H * W * t.a.ld * sizeof(bf16));
+  return t;
+}
+Tensor Engine::chan_view(const Tensor& t, int c0, int C) {
+  Tensor v = t;
+  v.a.p = t.a.p + c0;
+  v.a.C = C;
+  return v;
+}
+
+int Engine::set_weight(const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!key || !data || ndim < 1 || ndim > 4) return fail(FPNMT_ERR_INVALID, "set_weight: bad arguments");
+  HostW w;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    w.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  w.data.assign(data, data + n);
+  hw_[key] = std::move(w);
+  return 0;
+}
+const HostW* Engine::W(const std::string& key) {
+  auto it = hw_.find(key);
+  if (it == hw_.end()) {
+    set_last_error("missing weight: " + key);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+int Engine::upload_f32(const std::vector<float>& v, float** out) {
+  *out = (float*)dalloc(std::max<size_t>(v.size(), 4) * sizeof(float));
+  if (!*out) return FPNMT_ERR_CUDA;
+  FPNMT_CUDA_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+int Engine::prep_vec(const std::string& key, float** out) {
+  const HostW* w = W(key);
+  if (!w) return FPNMT_ERR_MISSING;
+  return upload_f32(w->data, out);
+}
+
+static inline uint16_t f2bf(float f) {   // round-to-nearest-even, matches __float2bfloat16_rn for finite values
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+int Engine::upload_gemm(const std::vector<float>& wt, const std::vector<float>& bias, int Cout, int K, GemmW* out) {
+  if (K % 8) return fail(FPNMT_ERR_INVALID, "upload_gemm: K must be a multiple of 8");
+  const size_t ldw = split_ ? 2 * (size_t)K : (size_t)K;
+  std::vector<uint16_t> h((size_t)Cout * ldw);
+  for (int r = 0; r < Cout; ++r)
+    for (int k = 0; k < K; ++k) {
+      const float f = wt[(size_t)r * K + k];
+      const uint16_t hi = f2bf(f);
+      h[r * ldw + k] = hi;
+      if (split_) h[r * ldw + K + k] = f2bf(f - bf2f(hi));
+    }
+  out->w = (bf16*)dalloc(h.size() * 2);
+  if (!out->w) return FPNMT_ERR_CUDA;
+  FPNMT_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> b = bias;
+  b.resize((size_t)(Cout + 7) / 8 * 8, 0.f);
+  RC(upload_f32(b, &out->bias));
+  out->Cout = Cout;
+  out->K = K;
+  return 0;
+}
+
+// Conv2D kernel (kh,kw,Cin,Cout) [+bias] [+ following inference BatchNorm folded] -> Wt[Cout][kh*kw*Cin (padded to kpad)]
+int Engine::prep_conv(const std::string& kernel_key, const std::string& bias_key, const std::string& bn, float eps,
+                      GemmW* out, int kpad) {
+  const HostW* k = W(kernel_key);
+  if (!k) return FPNMT_ERR_MISSING;
+  if (k->shape.size() != 4) return fail(FPNMT_ERR_INVALID, kernel_key + ": conv kernel must be rank 4");
+  const int kh = (int)k->shape[0], kw = (int)k->shape[1], cin = (int)k->shape[2], cout = (int)k->shape[3];
+  const int K = kh * kw * cin;
+  const int Kp = kpad ? kpad : K;
+  std::vector<float> scale(cout, 1.f), shift(cout, 0.f);
+  if (!bias_key.empty()) {
+    const HostW* b = W(bias_key);
+    if (!b) return FPNMT_ERR_MISSING;
+    for (int o = 0; o < cout; ++o) shift[o] = b->data[o];
+  }
+  if (!bn.empty()) {
+    const HostW *g = W(bn + "/gamma"), *be = W(bn + "/beta"), *m = W(bn + "/moving_mean"), *v = W(bn + "/moving_variance");
+    if (!g || !be || !m || !v) return FPNMT_ERR_MISSING;
+    for (int o = 0; o < cout; ++o) {
+      const float s = g->data[o] / sqrtf(v->data[o] + eps);
+      shift[o] = (shift[o] - m->data[o]) * s + be->data[o];
+      scale[o] = s;
+    }
+  }
+  std::vector<float> wt((size_t)cout * Kp, 0.f);
+  for (int t = 0; t < kh * kw; ++t)
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = &k->data[((size_t)t * cin + ci) * cout];
+      for (int o = 0; o < cout; ++o) wt[(size_t)o * Kp + (size_t)t * cin + ci] = src[o] * scale[o];
+    }
+  return upload_gemm(wt, shift, cout, Kp, out);
+}
+
+// Dense layers sharing one input, concatenated along the output axis: Wt[sum out][in]
+int Engine::prep_dense_cat(const std::vector<std::string>& names, GemmW* out) {
+  int in = -1, tot = 0;
+  for (auto& n : names) {
+    const HostW* k = W(n + "/kernel");
+    if (!k) return FPNMT_ERR_MISSING;
+    if (in < 0) in = (int)k->shape[0];
+    if ((int)k->shape[0] != in) return fail(FPNMT_ERR_INVALID, "prep_dense_cat: input dims differ");
+    tot += (int)k->shape[1];
+  }
+  std::vector<float> wt((size_t)tot * in), bias(tot);
+  int o0 = 0;
+  for (auto& n : names) {
+    const HostW *k = W(n + "/kernel"), *b = W(n + "/bias");
+    if (!b) return FPNMT_ERR_MISSING;
+    const int co = (int)k->shape[1];
+    for (int i = 0; i < in; ++i)
+      for (int o = 0; o < co; ++o) wt[(size_t)(o0 + o) * in + i] = k->data[(size_t)i * co + o];
+    for (int o = 0; o < co; ++o) bias[o0 + o] = b->data[o];
+    o0 += co;
+  }
+  return upload_gemm(wt, bias, tot, in, out);
+}
+
+// Dense layers whose outputs are summed, inputs concatenated: y = [x0|x1|..] @ [W0;W1;..] + sum(b)
+int Engine::prep_dense_stack(const std::vector<std::string>& names, GemmW* out) {
+  int co = -1, tot = 0;
+  for (auto& n : names) {
+    const HostW* k = W(n + "/kernel");
+    if (!k) return FPNMT_ERR_MISSING;
+    if (co < 0) co = (int)k->shape[1];
+    tot += (int)k->shape[0];
+  }
+  std::vector<float> wt((size_t)co * tot), bias(co, 0.f);
+  int i0 = 0;
+  for (auto& n : names) {
+    const HostW *k = W(n + "/kernel"), *b = W(n + "/bias");
+    if (!b) return FPNMT_ERR_MISSING;
+    const int in = (int)k->shape[0];
+    for (int i = 0; i < in; ++i)
+      for (int o = 0; o < co; ++o) wt[(size_t)o * tot + i0 + i] = k->data[(size_t)i * co + o];
+    for (int o = 0; o < co; ++o) bias[o] += b->data[o];
+    i0 += in;
+  }
+  return upload_gemm(wt, bias, co, tot, out);
+}
+
+int Engine::prep_bn_affine(const std::string& bn, float eps, int C, float** scale, float** shift) {
+  const HostW *g = W(bn + "/gamma"), *be = W(bn + "/beta"), *m = W(bn + "/moving_mean"), *v = W(bn + "/moving_variance");
+  if (!g || !be || !m || !v) return FPNMT_ERR_MISSING;
+  std::vector<float> s(C), t(C);
+  for (int c = 0; c < C; ++c) {
+    s[c] = g->data[c] / sqrtf(v->data[c] + eps);
+    t[c] = be->data[c] - m->data[c] * s[c];
+  }
+  RC(upload_f32(s, scale));
+  return upload_f32(t, shift);
+}
+
+int Engine::prep_depthwise(const std::string& key, const std::string& bn, float eps, float** w, float** bias) {
+  const HostW* k = W(key);
+  if (!k) return FPNMT_ERR_MISSING;
+  const int C = (int)k->shape[2];
+  const HostW *g = W(bn + "/gamma"), *be = W(bn + "/beta"), *m = W(bn + "/moving_mean"), *v = W(bn + "/moving_variance");
+  if (!g || !be || !m || !v) return FPNMT_ERR_MISSING;
+  std::vector<float> wt(9 * (size_t)C), b(C);
+  for (int c = 0; c < C; ++c) {
+    const float s = g->data[c] / sqrtf(v->data[c] + eps);
+    for (int t = 0; t < 9; ++t) wt[(size_t)t * C + c] = k->data[(size_t)t * C + c] * s;
+    b[c] = be->data[c] - m->data[c] * s;
+  }
+  RC(upload_f32(wt, w));
+  return upload_f32(b, bias);
+}
+
+// --------------------------------------------------------------------------------------------- op builders
+int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int kh, int kw, int pad_t,
+                     int pad_l, int act, int res_mode, const Tensor* res, const Tensor& out, float* out_f32, int ld_f32) {
+  if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
+  ConvGeom g{in.N, in.H, in.W, in.a.C, gw.Cout, kh, kw, pad_t, pad_l};
+  if (gw.K < kh * kw * in.a.C) return fail(FPNMT_ERR_INVALID, name + ": weight K smaller than kh*kw*Cin");
+  IgemmOp op;
+  Act r{nullptr, 0, 0, 0};
+  if (res) r = res->a;
+  // a K-padded weight (stem im2col) is addressed with Cin == K
+  RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_));
+  Op o;
+  o.name = name;
+  o.kind = "igemm";
+  o.flops = op.flops * (split_ ? 3.0 : 1.0);
+  const double esz = split_ ? 4.0 : 2.0;
+  o.bytes = (double)in.pixels() * in.a.C * esz + (double)gw.Cout * gw.K * esz +
+            (double)in.pixels() * gw.Cout * (out_f32 ? 4.0 : esz) + (res ? (double)res->pixels() * gw.Cout * esz : 0.0);
+  o.run = [op](cudaStream_t s) { return igemm_launch(op, s); };
+  prog.push_back(std::move(o));
+  return 0;
+}
+
+static Op ew_op(const std::string& name, std::function<int(cudaStream_t)> fn, double bytes, const char* kind = "elementwise") {
+  Op o;
+  o.name = name;
+  o.kind = kind;
+  o.run = std::move(fn);
+  o.bytes = bytes;
+  return o;
+}
+
+// im2col + GEMM stem for the Cin=3 first convolution (7x7 s2 pad 3 for ResNet/DenseNet)
+int Engine::build_stem_resnet_like(Program& p, const std::string& conv_key, const std::string& bn_key, float eps,
+                                   Tensor* out) {
+  const int B = cfg_.batch, S = cfg_.image_size, So = S / 2;
+  const int Kp = 152;   // 7*7*3 = 147 padded to a multiple of 8
+  Tensor col = new_act(1, 1, B * So * So, Kp);
+  const float** slot = img_slot_;
+  Act ca = col.a;
+  p.push_back(ew_op("stem_im2col", [=](cudaStream_t s) { return launch_im2col_stem(slot, B, S, S, 7, 7, 2, 3, 3, So, So, ca, s); },
+                    (double)B * S * S * 3 * 4 + (double)col.pixels() * Kp * (split_ ? 4 : 2)));
+  GemmW gw;
+  RC(prep_conv(conv_key, "", bn_key, eps, &gw, Kp));
+  Tensor y = new_act(B, So, So, 64);
+  Tensor yrows = y;
+  yrows.N = 1; yrows.H = 1; yrows.W = B * So * So;
+  RC(add_conv(p, "stem_conv", col, gw, 1, 1, 0, 0, ACT_RELU, RES_NONE, nullptr, yrows));
+  // the GEMM saw K = Kp input channels
+  *out = y;
+  return 0;
+}
+
+int Engine::build_resnet50(Program& p, Tensor c[3]) {
+  const int B = cfg_.batch;
+  Tensor x;
+  RC(build_stem_resnet_like(p, RN + "/conv1/kernel", RN + "/bn_conv1", 1e-5f, &x));
+  {   // pool1: 3x3 s2 'same' (even size -> pad bottom/right only)
+    Tensor y = new_act(B, x.H / 2, x.W / 2, 64);
+    Act xa = x.a, ya = y.a;
+    const int H = x.H, W = x.W;
+    p.push_back(ew_op("pool1", [=](cudaStream_t s) { return launch_maxpool(xa, B, H, W, 3, 2, 0, 0, H / 2, W / 2, false, ya, s); },
+                      (double)x.pixels() * 64 * 2 * 1.25));
+    x = y;
+  }
+  const int nblk[4] = {3, 4, 6, 3};
+  int ti = 0;
+  for (int st = 0; st < 4; ++st) {
+    const int f = 64 << st;
+    for (int b = 0; b < nblk[st]; ++b) {
+      char nm[8];
+      snprintf(nm, sizeof nm, "%d%c", st + 2, 'a' + b);
+      const std::string n(nm);
+      Tensor xin = x;
+      if (b == 0 && st > 0) {   // stride 2 on the first 1x1 (and on the shortcut): subsample once
+        Tensor sub = new_act(B, x.H / 2, x.W / 2, x.a.C);
+        Act xa = x.a, sa = sub.a;
+        const int H = x.H, W = x.W;
+        p.push_back(ew_op("res" + n + "_subsample", [=](cudaStream_t s) { return launch_subsample2(xa, B, H, W, sa, s); },
+                          (double)sub.pixels() * x.a.C * 4));
+        xin = sub;
+      }
+      GemmW wa, wb, wc;
+      RC(prep_conv(RN + "/res" + n + "_branch2a/kernel", "", RN + "/bn" + n + "_branch2a", 1e-5f, &wa));
+      RC(prep_conv(RN + "/res" + n + "_branch2b/kernel", "", RN + "/bn" + n + "_branch2b", 1e-5f, &wb));
+      RC(prep_conv(RN + "/res" + n + "_branch2c/kernel", "", RN + "/bn" + n + "_branch2c", 1e-5f, &wc));
+      Tensor ya = new_act(B, xin.H, xin.W, f), yb = new_act(B, xin.H, xin.W, f), yc = new_act(B, xin.H, xin.W, 4 * f);
+      RC(add_conv(p, "res" + n + "_2a", xin, wa, 1, 1, 0, 0, ACT_RELU, RES_NONE, nullptr, ya));
+      RC(add_conv(p, "res" + n + "_2b", ya, wb, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, yb));
+      Tensor sc = xin;
+      if (b == 0) {
+        GemmW w1;
+        RC(prep_conv(RN + "/res" + n + "_branch1/kernel", "", RN + "/bn" + n + "_branch1", 1e-5f, &w1));
+        sc = new_act(B, xin.H, xin.W, 4 * f);
+        RC(add_conv(p, "res" + n + "_1", xin, w1, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, sc));
+      }
+      RC(add_conv(p, "res" + n + "_2c", yb, wc, 1, 1, 0, 0, ACT_RELU, RES_SAME, &sc, yc));
+      x = yc;
+    }
+    if (st >= 1) c[ti++] = x;
+  }
+  return 0;
+}
+
+int Engine::build_mobilenetv2(Program& p, Tensor c[3]) {
+  const int B = cfg_.batch, S = cfg_.image_size, So = S / 2;
+  const float eps = 1e-3f;
+  // Conv1: ZeroPadding2D(((0,1),(0,1))) + 3x3 s2 valid
+  const int Kp = 32;
+  Tensor col = new_act(1, 1, B * So * So, Kp);
+  {
+    const float** slot = img_slot_;
+    Act ca = col.a;
+    p.push_back(ew_op("Conv1_im2col", [=](cudaStream_t s) { return launch_im2col_stem(slot, B, S, S, 3, 3, 2, 0, 0, So, So, ca, s); },
+                      (double)B * S * S * 3 * 4 + (double)col.pixels() * Kp * (split_ ? 4 : 2)));
+  }
+  GemmW g1;
+  RC(prep_conv(RN + "/Conv1/kernel", "", RN + "/bn_Conv1", eps, &g1, Kp));
+  Tensor x = new_act(B, So, So, 32);
+  {
+    Tensor xr = x;
+    xr.N = 1; xr.H = 1; xr.W = B * So * So;
+    RC(add_conv(p, "Conv1", col, g1, 1, 1, 0, 0, ACT_RELU6, RES_NONE, nullptr, xr));
+  }
+  auto depthwise = [&](const std::string& name, const Tensor& in, int stride, Tensor* out) -> int {
+    float *w, *b;
+    RC(prep_depthwise(RN + "/" + name + "/depthwise_kernel", RN + "/" + name + "_BN", eps, &w, &b));
+    const int Ho = in.H / stride, Wo = in.W / stride;
+    Tensor y = new_act(B, Ho, Wo, in.a.C);
+    Act ia = in.a, ya = y.a;
+    const int H = in.H, Wd = in.W;
+    const int pad = stride == 1 ? 1 : 0;
+    p.push_back(ew_op(name, [=](cudaStream_t s) { return launch_depthwise3x3(ia, B, H, Wd, stride, pad, pad, Ho, Wo, w, b, ACT_RELU6, ya, s); },
+                      ((double)in.pixels() + y.pixels()) * in.a.C * 2));
+    *out = y;
+    return 0;
+  };
+  {   // expanded_conv
+    Tensor d;
+    RC(depthwise("expanded_conv_depthwise", x, 1, &d));
+    GemmW gp;
+    RC(prep_conv(RN + "/expanded_conv_project/kernel", "", RN + "/expanded_conv_project_BN", eps, &gp));
+    Tensor y = new_act(B, d.H, d.W, 16);
+    RC(add_conv(p, "expanded_conv_project", d, gp, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, y));
+    x = y;
+  }
+  const int blocks[16][2] = {{24, 2}, {24, 1}, {32, 2}, {32, 1}, {32, 1}, {64, 2}, {64, 1}, {64, 1}, {64, 1}, {96, 1},
+                             {96, 1}, {96, 1}, {160, 2}, {160, 1}, {160, 1}, {320, 1}};
+  for (int k = 1; k <= 16; ++k) {
+    const int cout = blocks[k - 1][0], stride = blocks[k - 1][1];
+    const int cin = x.a.C;
+    const std::string pre = "block_" + std::to_string(k);
+    GemmW ge, gp;
+    RC(prep_conv(RN + "/" + pre + "_expand/kernel", "", RN + "/" + pre + "_expand_BN", eps, &ge));
+    Tensor e = new_act(B, x.H, x.W, 6 * cin);
+    RC(add_conv(p, pre + "_expand", x, ge, 1, 1, 0, 0, ACT_RELU6, RES_NONE, nullptr, e));
+    Tensor d;
+    RC(depthwise(pre + "_depthwise", e, stride, &d));
+    RC(prep_conv(RN + "/" + pre + "_project/kernel", "", RN + "/" + pre + "_project_BN", eps, &gp));
+    Tensor y = new_act(B, d.H, d.W, cout);
+    const bool add = (stride == 1 && cin == cout);
+    RC(add_conv(p, pre + "_project", d, gp, 1, 1, 0, 0, ACT_NONE, add ? RES_SAME : RES_NONE, add ? &x : nullptr, y));
+    x = y;
+    if (k == 5) c[0] = x;    // block_5_add
+    if (k == 12) c[1] = x;   // block_12_add
+  }
+  GemmW gl;
+  RC(prep_conv(RN + "/Conv_1/kernel", "", RN + "/Conv_1_bn", eps, &gl));
+  Tensor y = new_act(B, x.H, x.W, 1280);
+  RC(add_conv(p, "Conv_1", x, gl, 1, 1, 0, 0, ACT_RELU6, RES_NONE, nullptr, y));
+  c[2] = y;                  // out_relu
+  return 0;
+}
+
+int Engine::build_densenet121(Program& p, Tensor c[3]) {
+  const int B = cfg_.batch;
+  const float eps = 1.001e-5f;
+  Tensor x;
+  RC(build_stem_resnet_like(p, RN + "/conv1/conv/kernel", RN + "/conv1/bn", eps, &x));
+  const int nblk[4] = {6, 12, 24, 16};
+  int cch = 64;
+  int H = x.H / 2, Wd = x.W / 2;
+  Tensor buf = new_act(B, H, Wd, cch + 32 * nblk[0]);
+  {   // pool1: ZeroPadding2D(1) + 3x3 s2 valid, written into the first 64 channels of the stage buffer
+    Act xa = x.a, ya = chan_view(buf, 0, 64).a;
+    const int Hi = x.H, Wi = x.W;
+    p.push_back(ew_op("pool1", [=](cudaStream_t s) { return launch_maxpool(xa, B, Hi, Wi, 3, 2, 1, 1, Hi / 2, Wi / 2, true, ya, s); },
+                      (double)x.pixels() * 64 * 2 * 1.25));
+  }
+  int ti = 0;
+  for (int si = 0; si < 4; ++si) {
+    const int stage = si + 2;
+    for (int b = 1; b <= nblk[si]; ++b) {
+      const std::string pre = RN + "/conv" + std::to_string(stage) + "_block" + std::to_string(b);
+      const std::string sn = "conv" + std::to_string(stage) + "_block" + std::to_string(b);
+      float *sc, *sh;
+      RC(prep_bn_affine(pre + "_0_bn", eps, cch, &sc, &sh));
+      Tensor t0 = new_act(B, H, Wd, cch);
+      Act ia = chan_view(buf, 0, cch).a, ta = t0.a;
+      const size_t pix = t0.pixels();
+      p.push_back(ew_op(sn + "_0_bn_relu", [=](cudaStream_t s) { return launch_scale_shift_relu(ia, pix, sc, sh, ta, s); },
+                        (double)pix * cch * 4));
+      GemmW g1, g2;
+      RC(prep_conv(pre + "_1_conv/kernel", "", pre + "_1_bn", eps, &g1));
+      RC(prep_conv(pre + "_2_conv/kernel", "", "", 0.f, &g2));
+      Tensor y1 = new_act(B, H, Wd, 128);
+      RC(add_conv(p, sn + "_1_conv", t0, g1, 1, 1, 0, 0, ACT_RELU, RES_NONE, nullptr, y1));
+      RC(add_conv(p, sn + "_2_conv", y1, g2, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, chan_view(buf, cch, 32)));
+      cch += 32;
+    }
+    if (si >= 1) c[ti++] = chan_view(buf, 0, cch);
+    if (si < 3) {
+      const std::string pre = RN + "/pool" + std::to_string(stage);
+      float *sc, *sh;
+      RC(prep_bn_affine(pre + "_bn", eps, cch, &sc, &sh));
+      Tensor t0 = new_act(B, H, Wd, cch);
+      Act ia = chan_view(buf, 0, cch).a, ta = t0.a;
+      const size_t pix = t0.pixels();
+      p.push_back(ew_op("pool" + std::to_string(stage) + "_bn_relu",
+                        [=](cudaStream_t s) { return launch_scale_shift_relu(ia, pix, sc, sh, ta, s); }, (double)pix * cch * 4));
+      GemmW g;
+      RC(prep_conv(pre + "_conv/kernel", "", "", 0.f, &g));
+      Tensor y = new_act(B, H, Wd, cch / 2);
+      RC(add_conv(p, "pool" + std::to_string(stage) + "_conv", t0, g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, y));
+      cch /= 2;
+      Tensor nbuf = new_act(B, H / 2, Wd / 2, cch + 32 * nblk[si + 1]);
+      Act ya = y.a, na = chan_view(nbuf, 0, cch).a;
+      const int Hi = H, Wi = Wd;
+      p.push_back(ew_op("pool" + std::to_string(stage) + "_pool", [=](cudaStream_t s) { return launch_avgpool2(ya, B, Hi, Wi, na, s); },
+                        (double)y.pixels() * cch * 2 * 1.25));
+      buf = nbuf;
+      H /= 2;
+      Wd /= 2;
+    }
+  }
+  return 0;
+}
+
+// FPN (retinanet.py:105-141) + per-level head sub-model (retinanet.py:283-301) + token pre-amble (transformer.py:279-296)
+int Engine::build_fpn_heads(Program& p, Tensor c[3]) {
+  const int B = cfg_.batch;
+  const int F = 256, D = cfg_.d_model;
+  taps_["C3"] = c[0]; taps_["C4"] = c[1]; taps_["C5"] = c[2];
+  GemmW c5r, p5w, c4r, p4w, c3r, p3w, p6w, p7w;
+  RC(prep_conv(RN + "/C5_reduced/kernel", RN + "/C5_reduced/bias", "", 0, &c5r));
+  RC(prep_conv(RN + "/P5/kernel", RN + "/P5/bias", "", 0, &p5w));
+  RC(prep_conv(RN + "/C4_reduced/kernel", RN + "/C4_reduced/bias", "", 0, &c4r));
+  RC(prep_conv(RN + "/P4/kernel", RN + "/P4/bias", "", 0, &p4w));
+  RC(prep_conv(RN + "/C3_reduced/kernel", RN + "/C3_reduced/bias", "", 0, &c3r));
+  RC(prep_conv(RN + "/P3/kernel", RN + "/P3/bias", "", 0, &p3w));
+  RC(prep_conv(RN + "/conv2d/kernel", RN + "/conv2d/bias", "", 0, &p6w));
+  RC(prep_conv(RN + "/conv2d_1/kernel", RN + "/conv2d_1/bias", "", 0, &p7w));
+  Tensor P[5];
+  Tensor p5f = new_act(B, c[2].H, c[2].W, F);
+  RC(add_conv(p, "C5_reduced", c[2], c5r, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, p5f));
+  P[2] = new_act(B, p5f.H, p5f.W, F);
+  RC(add_conv(p, "P5", p5f, p5w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, P[2]));
+  Tensor p4m = new_act(B, c[1].H, c[1].W, F);   // lateral 1x1 with the nearest-2x upsample + add fused into the epilogue
+  RC(add_conv(p, "C4_reduced+P5_upsampled", c[1], c4r, 1, 1, 0, 0, ACT_NONE, RES_UP2, &p5f, p4m));
+  P[1] = new_act(B, p4m.H, p4m.W, F);
+  RC(add_conv(p, "P4", p4m, p4w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, P[1]));
+  Tensor p3m = new_act(B, c[0].H, c[0].W, F);
+  RC(add_conv(p, "C3_reduced+P4_upsampled", c[0], c3r, 1, 1, 0, 0, ACT_NONE, RES_UP2, &p4m, p3m));
+  P[0] = new_act(B, p3m.H, p3m.W, F);
+  RC(add_conv(p, "P3", p3m, p3w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, P[0]));
+  auto pool2 = [&](const std::string& name, const Tensor& in, Tensor* out) {
+    Tensor y = new_act(B, in.H / 2, in.W / 2, in.a.C);
+    Act ia = in.a, ya = y.a;
+    const int H = in.H, W = in.W;
+    p.push_back(ew_op(name, [=](cudaStream_t s) { return launch_maxpool(ia, B, H, W, 2, 2, 0, 0, H / 2, W / 2, false, ya, s); },
+                      (double)in.pixels() * in.a.C * 2 * 1.25));
+    *out = y;
+  };
+  {
+    Tensor t = new_act(B, p5f.H, p5f.W, F);
+    RC(add_conv(p, "P6_conv", p5f, p6w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, t));
+    pool2("P6", t, &P[3]);
+    Tensor t2 = new_act(B, P[3].H, P[3].W, F);
+    RC(add_conv(p, "P7_conv", P[3], p7w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, t2));
+    pool2("P7", t2, &P[4]);
+  }
+  const char* pn[5] = {"P3", "P4", "P5", "P6", "P7"};
+  for (int i = 0; i < 5; ++i) taps_[pn[i]] = P[i];
+
+  // shared head weights
+  GemmW t0w, r1w, c1w, scw, clw, h4w, h5w;
+  {   // first trunk convs of both sub-models share their input: one conv with Cout = 512 ([reg | cls])
+    const HostW *kr = W(RN + "/regression_submodel/pyramid_regression_0/kernel"), *br = W(RN + "/regression_submodel/pyramid_regression_0/bias");
+    const HostW *kc = W(RN + "/classification_submodel/pyramid_classification_0/kernel"), *bc = W(RN + "/classification_submodel/pyramid_classification_0/bias");
+    if (!kr || !br || !kc || !bc) return FPNMT_ERR_MISSING;
+    const int K = 9 * F;
+    std::vector<float> wt((size_t)2 * F * K), bias(2 * F);
+    for (int t = 0; t < 9; ++t)
+      for (int ci = 0; ci < F; ++ci)
+        for (int o = 0; o < F; ++o) {
+          wt[(size_t)o * K + t * F + ci] = kr->data[((size_t)t * F + ci) * F + o];
+          wt[(size_t)(F + o) * K + t * F + ci] = kc->data[((size_t)t * F + ci) * F + o];
+        }
+    for (int o = 0; o < F; ++o) {
+      bias[o] = br->data[o];
+      bias[F + o] = bc->data[o];
+    }
+    RC(upload_gemm(wt, bias, 2 * F, K, &t0w));
+  }
+  RC(prep_conv(RN + "/regression_submodel/pyramid_regression_1/kernel", RN + "/regression_submodel/pyramid_regression_1/bias", "", 0, &r1w));
+  RC(prep_conv(RN + "/classification_submodel/pyramid_classification_1/kernel", RN + "/classification_submodel/pyramid_classification_1/bias", "", 0, &c1w));
+  RC(prep_conv(HM + "/conv2d_2/kernel", HM + "/conv2d_2/bias", "", 0, &scw));
+  RC(prep_conv(HM + "/conv2d_3/kernel", HM + "/conv2d_3/bias", "", 0, &clw));
+  RC(prep_conv(HM + "/conv2d_4/kernel", HM + "/conv2d_4/bias", "", 0, &h4w));
+  RC(prep_conv(HM + "/conv2d_5/kernel", HM + "/conv2d_5/bias", "", 0, &h5w));
+
+  for (int i = 0; i < 5; ++i) {
+    const std::string L = pn[i];
+    const Tensor& x = P[i];
+    Tensor t0 = new_act(B, x.H, x.W, 2 * F);
+    RC(add_conv(p, L + "_trunk0", x, t0w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, t0));
+    Tensor r1 = new_act(B, x.H, x.W, F), c1 = new_act(B, x.H, x.W, F);
+    RC(add_conv(p, L + "_reg1", chan_view(t0, 0, F), r1w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, r1));
+    RC(add_conv(p, L + "_cls1", chan_view(t0, F, F), c1w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, c1));
+    Tensor score = new_act(B, x.H, x.W, 1), cmap = new_act(B, x.H, x.W, F);
+    RC(add_conv(p, L + "_score", r1, scw, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, score));
+    RC(add_conv(p, L + "_clsmap", c1, clw, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, cmap));
+    Tensor co = new_act(B, x.H, x.W, F);
+    {
+      Act sa = score.a, ca = cmap.a, oa = co.a;
+      const int HW = x.H * x.W;
+      p.push_back(ew_op(L + "_coattention", [=](cudaStream_t s) { return launch_coattention(sa, ca, B, HW, oa, s); },
+                        (double)co.pixels() * F * 4));
+    }
+    Tensor h4 = new_act(B, x.H, x.W, F);
+    RC(add_conv(p, L + "_conv4", co, h4w, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, nullptr, h4));
+    Tensor hp;
+    pool2(L + "_pool", h4, &hp);
+    feat_[i] = new_act(B, hp.H, hp.W, D);
+    RC(add_conv(p, L + "_conv5", hp, h5w, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, nullptr, feat_[i]));
+    taps_["feat" + std::to_string(i)] = feat_[i];
+  }
+  return 0;
+}
+
+// Multi-Transformer encoder (transformer.py:266-303).  Views after reordering [P3,P4,P5,P7 | P6]: the four
+// static views feed K/V only, so their projections for all layers are hoisted into one GEMM per view.
+int Engine::build_mt_encoder(Program& p) {
+  const int B = cfg_.batch, D = cfg_.d_model, L = cfg_.num_layers, H = cfg_.num_heads, FF = cfg_.dff;
+  const int order[5] = {0, 1, 2, 4, 3};   // transformer.py:253 with BASELINE_INDEX = 3
+  // positional table (transformer.py:22-43), input_vocab_size = ceil(S/16)^2 (pipeline.py:20)
+  const int npos = ((cfg_.image_size + 15) / 16) * ((cfg_.image_size + 15) / 16);
+  std::vector<float> pos((size_t)npos * D);
+  for (int ps = 0; ps < npos; ++ps)
+    for (int i = 0; i < D; ++i) {
+      const double rate = 1.0 / pow(10000.0, (double)(2 * (i / 2)) / (double)(float)D);
+      const double ang = ps * rate;
+      pos[(size_t)ps * D + i] = (float)((i % 2 == 0) ? sin(ang) : cos(ang));
+    }
+  float *d_pos, *g0, *b0;
+  RC(upload_f32(pos, &d_pos));
+  RC(prep_vec(std::string(TR) + "/encoder/layernorm1/gamma", &g0));
+  RC(prep_vec(std::string(TR) + "/encoder/layernorm1/beta", &b0));
+  Tensor tok[5];
+  int ntok[5];
+  for (int v = 0; v < 5; ++v) {
+    const Tensor& f = feat_[order[v]];
+    ntok[v] = f.H * f.W;
+    tok[v] = rows_act(B * ntok[v], D);
+    Act fa = f.a, ta = tok[v].a;
+    const int hw = ntok[v];
+    p.push_back(ew_op("tokens" + std::to_string(v) + "_ln_pos",
+                      [=](cudaStream_t s) { return launch_tokens_ln_pos(fa, B, hw, g0, b0, 1e-6f, d_pos, ta, s); },
+                      (double)B * hw * D * 4));
+    taps_["tokens" + std::to_string(v)] = tok[v];
+  }
+  n_base_ = ntok[4];
+  if (n_base_ > 16) return fail(FPNMT_ERR_INVALID, "baseline view has more than 16 tokens (image_size > 512 unsupported)");
+  // hoisted K/V projections: per view one GEMM [B*n, 512] x [512, L*2*512]
+  Tensor kv[4];
+  for (int v = 0; v < 4; ++v) {
+    std::vector<std::string> names;
+    for (int l = 0; l < L; ++l) {
+      const std::string m = std::string(TR) + "/encoder/enc_layers/" + std::to_string(l) + "/mhas/" + std::to_string(v);
+      names.push_back(m + "/wk");
+      names.push_back(m + "/wv");
+    }
+    GemmW g;
+    RC(prep_dense_cat(names, &g));
+    kv[v] = rows_act(B * ntok[v], L * 2 * D);
+    RC(add_conv(p, "enc_kv_view" + std::to_string(v), tok[v], g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, kv[v]));
+  }
+  Tensor base = tok[4];
+  const int R = B * n_base_;
+  for (int l = 0; l < L; ++l) {
+    const std::string e = std::string(TR) + "/encoder/enc_layers/" + std::to_string(l);
+    const std::string ln = "enc" + std::to_string(l);
+    GemmW gq, go, g1, g2;
+    RC(prep_dense_cat({e + "/mhas/0/wq", e + "/mhas/1/wq", e + "/mhas/2/wq", e + "/mhas/3/wq"}, &gq));
+    RC(prep_dense_stack({e + "/mhas/0/dense", e + "/mhas/1/dense", e + "/mhas/2/dense", e + "/mhas/3/dense"}, &go));
+    RC(prep_dense_cat({e + "/ffn1"}, &g1));
+    RC(prep_dense_cat({e + "/ffn2"}, &g2));
+    Tensor q = rows_act(R, 4 * D), att = rows_act(R, 4 * D);
+    RC(add_conv(p, ln + "_q", base, gq, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, q));
+    for (int v = 0; v < 4; ++v) {
+      Act qa = q.a, ka = kv[v].a, oa = att.a;
+      const int tk = ntok[v], tq = n_base_, kc = l * 2 * D, vc = l * 2 * D + D, qc = v * D;
+      Op o = ew_op(ln + "_attn_view" + std::to_string(v),
+                   [=](cudaStream_t s) { return launch_enc_attention(qa, qc, ka, kc, vc, B, tq, tk, H, oa, qc, s); },
+                   (double)B * tk * 2 * D * 2, "attention");
+      o.flops = 4.0 * B * tq * tk * D;
+      p.push_back(std::move(o));
+    }
+    float* y = (float*)dalloc((size_t)R * D * 4);
+    Tensor none;
+    RC(add_conv(p, ln + "_out+res", att, go, 1, 1, 0, 0, ACT_NONE, RES_SAME, &base, none, y, D));
+    float *g1p, *b1p, *g2p, *b2p;
+    RC(prep_vec(e + "/layernorm1/gamma", &g1p));
+    RC(prep_vec(e + "/layernorm1/beta", &b1p));
+    RC(prep_vec(e + "/layernorm2/gamma", &g2p));
+    RC(prep_vec(e + "/layernorm2/beta", &b2p));
+    Tensor out1 = rows_act(R, D);
+    {
+      Act oa = out1.a;
+      p.push_back(ew_op(ln + "_ln1", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g1p, b1p, 1e-6f, oa, s); }, (double)R * D * 6));
+    }
+    Tensor hdn = rows_act(R, FF);
+    RC(add_conv(p, ln + "_ffn1", out1, g1, 1, 1, 0, 0, ACT_LEAKY, RES_NONE, nullptr, hdn));
+    float* y2 = (float*)dalloc((size_t)R * D * 4);
+    RC(add_conv(p, ln + "_ffn2+res", hdn, g2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out1, none, y2, D));
+    Tensor out2 = rows_act(R, D);
+    {
+      Act oa = out2.a;
+      p.push_back(ew_op(ln + "_ln2", [=](cudaStream_t s) { return launch_layernorm_rows(y2, R, D, g2p, b2p, 1e-6f, oa, s); }, (double)R * D * 6));
+    }
+    base = out2;
+    taps_["enc_layer" + std::to_string(l)] = out2;
+  }
+  enc_out_ = base;
+  taps_["memory"] = base;
+  return 0;
+}
+
+// KV-cached decoder step programs (transformer.py:224-243, 321-341, 372) + decode tail (pipeline.py:115-148)
+int Engine::build_decoder() {
+  const int B = cfg_.batch, N = cfg_.beam, D = cfg_.d_model, L = cfg_.num_layers, H = cfg_.num_heads, FF = cfg_.dff;
+  const int V = cfg_.vocab, T = cfg_.max_len;
+  const int R = B * N;
+  // beam state
+  bs_.B = B; bs_.N = N; bs_.V = V; bs_.T = T;
+  bs_.start_id = cfg_.start_id; bs_.end_id = cfg_.end_id;
+  bs_.prob_mode = cfg_.score_mode == FPNMT_SCORE_PROB;
+  for (int i = 0; i < 2; ++i) {
+    bs_.score[i] = (float*)dalloc((size_t)R * 4);
+    bs_.seq[i] = (int*)dalloc((size_t)R * (T + 1) * 4);
+    bs_.anc[i] = nullptr;
+  }
+  int* anc = (int*)dalloc((size_t)2 * R * T * 4);   // [2][R][T] contiguous (the attention kernel indexes by step&1)
+  bs_.anc[0] = anc;
+  bs_.anc[1] = anc + (size_t)R * T;
+  bs_.last_tok = (int*)dalloc((size_t)R * 4);
+  bs_.step = (int*)dalloc(16);
+  bs_.done = (int*)dalloc((size_t)B * 4);
+  bs_.n_done = (int*)dalloc(16);
+  bs_.out_ids = (int*)dalloc((size_t)B * T * 4);
+  bs_.out_len = (int*)dalloc((size_t)B * 4);
+  bs_.cand_val = (float*)dalloc((size_t)R * N * 4);
+  bs_.cand_idx = (int*)dalloc((size_t)R * N * 4);
+  step_scores_ = (float*)dalloc((size_t)T * B * 4);
+  bs_.step_logprob = step_scores_;
+  bs_.parent_out = (int*)dalloc((size_t)T * R * 4);
+  bs_.token_out = (int*)dalloc((size_t)T * R * 4);
+  logits_ = (float*)dalloc((size_t)R * V * 4);
+  forced_tokens_ = (int*)dalloc((size_t)B * T * 4);
+  forced_logits_ = nullptr;
+  if (!logits_ || !forced_tokens_) return FPNMT_ERR_CUDA;
+  FPNMT_CUDA_OK(cudaMemset(anc, 0, (size_t)2 * R * T * 4));
+
+  // decoder positional table (transformer.py:315)
+  std::vector<float> pos((size_t)T * D);
+  for (int ps = 0; ps < T; ++ps)
+    for (int i = 0; i < D; ++i) {
+      const double rate = 1.0 / pow(10000.0, (double)(2 * (i / 2)) / (double)(float)D);
+      pos[(size_t)ps * D + i] = (float)((i % 2 == 0) ? sin(ps * rate) : cos(ps * rate));
+    }
+  float *d_pos, *d_emb;
+  RC(upload_f32(pos, &d_pos));
+  RC(prep_vec(std::string(TR) + "/decoder/embedding/embeddings", &d_emb));
+
+  // cross-attention K/V of the memory for all layers: one GEMM [B*16,512] x [512, L*2*512] per batch
+  {
+    std::vector<std::string> names;
+    for (int l = 0; l < L; ++l) {
+      const std::string m = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l) + "/mha2";
+      names.push_back(m + "/wk");
+      names.push_back(m + "/wv");
+    }
+    GemmW g;
+    RC(prep_dense_cat(names, &g));
+    Tensor ckv = rows_act(B * n_base_, L * 2 * D);
+    RC(add_conv(dec_init_prog_, "dec_cross_kv", enc_out_, g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, ckv));
+    taps_["cross_kv"] = ckv;
+
+    Tensor x = rows_act(R, D);
+    const BeamState bs = bs_;
+    {
+      Act xa = x.a;
+      const int* tok = bs_.last_tok;
+      const int* step = bs_.step;
+      step_prog_.push_back(ew_op("embed_pos", [=](cudaStream_t s) { return launch_embed_pos(tok, d_emb, d_pos, step, R, D, xa, s); }, (double)R * D * 6));
+    }
+    Tensor none;
+    for (int l = 0; l < L; ++l) {
+      const std::string d = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l);
+      const std::string ln = "dec" + std::to_string(l);
+      GemmW gqkv, go1, gq2, go2, g1, g2;
+      RC(prep_dense_cat({d + "/mha1/wq", d + "/mha1/wk", d + "/mha1/wv"}, &gqkv));
+      RC(prep_dense_cat({d + "/mha1/dense"}, &go1));
+      RC(prep_dense_cat({d + "/mha2/wq"}, &gq2));
+      RC(prep_dense_cat({d + "/mha2/dense"}, &go2));
+      RC(prep_dense_cat({d + "/ffn1"}, &g1));
+      RC(prep_dense_cat({d + "/ffn2"}, &g2));
+      float* lnp[6];
+      const char* lnn[6] = {"/layernorm1/gamma", "/layernorm1/beta", "/layernorm2/gamma", "/layernorm2/beta", "/layernorm3/gamma", "/layernorm3/beta"};
+      for (int i = 0; i < 6; ++i) RC(prep_vec(d + lnn[i], &lnp[i]));
+      Tensor qkv = rows_act(R, 3 * D), att = rows_act(R, D), out1 = rows_act(R, D), q2 = rows_act(R, D), att2 = rows_act(R, D),
+             out2 = rows_act(R, D), hdn = rows_act(R, FF), out3 = rows_act(R, D);
+      Tensor kc = rows_act(R * T, D), vc = rows_act(R * T, D);
+      float* y = (float*)dalloc((size_t)R * D * 4);
+      RC(add_conv(step_prog_, ln + "_qkv", x, gqkv, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, qkv));
+      {
+        Act qa = qkv.a, ka = kc.a, va = vc.a, oa = att.a;
+        const int* ancp = anc;
+        const int* step = bs_.step;
+        Op o = ew_op(ln + "_self_attn", [=](cudaStream_t s) { return launch_dec_self_attention(qa, ka, va, ancp, step, R, T, H, oa, s); },
+                     (double)R * (T / 2) * 2 * D * 2, "attention");
+        step_prog_.push_back(std::move(o));
+      }
+      RC(add_conv(step_prog_, ln + "_o1+res", att, go1, 1, 1, 0, 0, ACT_NONE, RES_SAME, &x, none, y, D));
+      {
+        Act oa = out1.a;
+        float *g = lnp[0], *b = lnp[1];
+        step_prog_.push_back(ew_op(ln + "_ln1", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
+      }
+      RC(add_conv(step_prog_, ln + "_q2", out1, gq2, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, q2));
+      {
+        Act qa = q2.a, ka = ckv.a, oa = att2.a;
+        const int kcx = l * 2 * D, vcx = l * 2 * D + D, tk = n_base_;
+        step_prog_.push_back(ew_op(ln + "_cross_attn", [=](cudaStream_t s) { return launch_dec_cross_attention(qa, ka, kcx, vcx, R, N, tk, H, oa, s); },
+                                   (double)B * tk * 2 * D * 2, "attention"));
+      }
+      RC(add_conv(step_prog_, ln + "_o2+res", att2, go2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out1, none, y, D));
+      {
+        Act oa = out2.a;
+        float *g = lnp[2], *b = lnp[3];
+        step_prog_.push_back(ew_op(ln + "_ln2", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
+      }
+      RC(add_conv(step_prog_, ln + "_ffn1", out2, g1, 1, 1, 0, 0, ACT_LEAKY, RES_NONE, nullptr, hdn));
+      RC(add_conv(step_prog_, ln + "_ffn2+res", hdn, g2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out2, none, y, D));
+      {
+        Act oa = out3.a;
+        float *g = lnp[4], *b = lnp[5];
+        step_prog_.push_back(ew_op(ln + "_ln3", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
+      }
+      x = out3;
+    }
+    GemmW gf;
+    RC(prep_dense_cat({std::string(TR) + "/final_layer"}, &gf));
+    float* lg = logits_;
+    RC(add_conv(step_prog_, "final_layer", x, gf, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, none, lg, V));
+    step_forced_prog_ = step_prog_;   // shared prefix; the tails differ
+    {
+      Op o = ew_op("beam_rowtopk", [=](cudaStream_t s) { return launch_beam_rowtopk(bs, lg, V, s); }, (double)R * V * 4, "beam");
+      step_prog_.push_back(std::move(o));
+      Op m = ew_op("beam_merge", [=](cudaStream_t s) { return launch_beam_merge(bs, s); }, (double)R * (T + 1) * 8, "beam");
+      m.idempotent = false;
+      step_prog_.push_back(std::move(m));
+    }
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------- finalize / run
+int Engine::finalize() {
+  if (finalized_) return fail(FPNMT_ERR_STATE, "finalize_weights called twice");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  img_slot_ = (const float**)dalloc(16);
+  if (!img_slot_) return FPNMT_ERR_CUDA;
+  Tensor c[3];
+  if (cfg_.backbone == FPNMT_BACKBONE_RESNET50) RC(build_resnet50(cnn_prog_, c));
+  else if (cfg_.backbone == FPNMT_BACKBONE_MOBILENETV2) RC(build_mobilenetv2(cnn_prog_, c));
+  else RC(build_densenet121(cnn_prog_, c));
+  RC(build_fpn_heads(cnn_prog_, c));
+  enc_prog_ = cnn_prog_;
+  RC(build_mt_encoder(enc_prog_));
+  RC(build_decoder());
+  FPNMT_CUDA_OK(cudaDeviceSynchronize());
+  hw_.clear();   // host staging no longer needed
+  finalized_ = true;
+  return 0;
+}
+
+int Engine::run_program(Program& p, cudaStream_t s) {
+  for (auto& op : p) {
+    int rc = op.run(s);
+    if (rc) {
+      set_last_error("op '" + op.name + "' failed: " + fpnmt_last_error());
+      return rc;
+    }
+  }
+  launches += (int64_t)p.size();
+  return 0;
+}
+
+int Engine::capture(Program& p, cudaGraphExec_t* out) {
+  cudaGraph_t g;
+  FPNMT_CUDA_OK(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (auto& op : p) {
+    rc = op.run(cap_stream_);
+    if (rc) break;
+  }
+  cudaError_t e = cudaStreamEndCapture(cap_stream_, &g);
+  if (rc) return rc;
+  FPNMT_CUDA_OK(e);
+  FPNMT_CUDA_OK(cudaGraphInstantiate(out, g, 0));
+  FPNMT_CUDA_OK(cudaGraphDestroy(g));
+  return 0;
+}
+
+int Engine::launch_prog(Program& p, cudaGraphExec_t g, cudaStream_t s) {
+  if (g) {
+    FPNMT_CUDA_OK(cudaGraphLaunch(g, s));
+    launches += (int64_t)p.size();
+    return 0;
+  }
+  return run_program(p, s);
+}
+
+int Engine::set_images(const float* images, int on_host, cudaStream_t s) {
+  const size_t n = (size_t)cfg_.batch * cfg_.image_size * cfg_.image_size * 3;
+  const float* dptr = images;
+  if (on_host) {
+    if (!img_stage_) {
+      img_stage_ = (float*)dalloc(n * 4);
+      if (!img_stage_) return FPNMT_ERR_CUDA;
+    }
+    FPNMT_CUDA_OK(cudaMemcpyAsync(img_stage_, images, n * 4, cudaMemcpyHostToDevice, s));
+    dptr = img_stage_;
+  }
+  FPNMT_CUDA_OK(cudaMemcpyAsync(img_slot_, &dptr, sizeof(dptr), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int Engine::encode(const float* images, int on_host, float* memory_out, cudaStream_t s, bool cnn_only) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "encode before finalize_weights");
+  if (!images) return fail(FPNMT_ERR_INVALID, "images is NULL");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  RC(set_images(images, on_host, s));
+  if (cfg_.use_graphs) {
+    if (cnn_only && !cnn_graph_) RC(capture(cnn_prog_, &cnn_graph_));
+    if (!cnn_only && !enc_graph_) RC(capture(enc_prog_, &enc_graph_));
+  }
+  if (cnn_only) RC(launch_prog(cnn_prog_, cnn_graph_, s));
+  else RC(launch_prog(enc_prog_, enc_graph_, s));
+  if (memory_out && !cnn_only) RC(launch_act_to_f32(enc_out_.a, enc_out_.pixels(), memory_out, s));
+  return 0;
+}
+
+int Engine::features(const float* images, int on_host, float* const out5[5], cudaStream_t s) {
+  RC(encode(images, on_host, nullptr, s, true));
+  for (int i = 0; i < 5; ++i)
+    if (out5[i]) RC(launch_act_to_f32(feat_[i].a, feat_[i].pixels(), out5[i], s));
+  return 0;
+}
+
+int Engine::get_tap(const char* name, float* out, size_t cap, size_t* count, cudaStream_t s) {
+  auto it = taps_.find(name);
+  if (it == taps_.end()) return fail(FPNMT_ERR_INVALID, std::string("unknown tap: ") + name);
+  const Tensor& t = it->second;
+  const size_t n = t.pixels() * t.a.C;
+  if (count) *count = n;
+  if (!out) return 0;
+  if (cap < n) return fail(FPNMT_ERR_INVALID, "get_tap: buffer too small");
+  return launch_act_to_f32(t.a, t.pixels(), out, s);
+}
+
+// teacher-forced tail: copy beam-0 logits of every image to logits_out[b][t][:], feed the next forced token
+__global__ void k_forced_tail(BeamState st, const float* __restrict__ logits, const int* __restrict__ forced, int tlen,
+                              float* __restrict__ out) {
+  const int t = *st.step;
+  const int b = blockIdx.x;
+  const float* src = logits + (size_t)(b * st.N) * st.V;
+  float* dst = out + ((size_t)b * tlen + t) * st.V;
+  for (int i = threadIdx.x; i < st.V; i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x < st.N && t + 1 < tlen) st.last_tok[b * st.N + threadIdx.x] = forced[(size_t)b * tlen + t + 1];
+}
+__global__ void k_forced_init(BeamState st, const int* __restrict__ forced, int tlen) {
+  const int rows = st.B * st.N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *st.step = 0;
+  if (i < rows) st.last_tok[i] = forced[(size_t)(i / st.N) * tlen];
+  for (size_t j = i; j < (size_t)2 * rows * st.T; j += (size_t)gridDim.x * blockDim.x)
+    st.anc[0][j] = (int)((j / st.T) % rows);   // identity ancestry in both buffers
+}
+__global__ void k_step_inc(int* step) { *step += 1; }
+__global__ void k_anc_identity(int* anc, int rows, int T) {
+  const size_t n = (size_t)2 * rows * T;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+    anc[j] = (int)((j / T) % rows);
+}
+
+int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "decode_logits before finalize_weights");
+  if (t < 1 || t > cfg_.max_len) return fail(FPNMT_ERR_INVALID, "decode_logits: t out of range");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  const int R = cfg_.batch * cfg_.beam;
+  if (memory) RC(launch_f32_to_act(memory, enc_out_.pixels(), cfg_.d_model, enc_out_.a, s));
+  RC(run_program(dec_init_prog_, s));
+  k_forced_init<<<(R + 255) / 256, 256, 0, s>>>(bs_, tokens, t);
+  FPNMT_CUDA_OK(cudaGetLastError());
+  for (int i = 0; i < t; ++i) {
+    RC(run_program(step_forced_prog_, s));
+    k_forced_tail<<<cfg_.batch, 256, 0, s>>>(bs_, logits_, tokens, t, logits_out);
+    k_step_inc<<<1, 1, 0, s>>>(bs_.step);
+    FPNMT_CUDA_OK(cudaGetLastError());
+    launches += 2;
+  }
+  return 0;
+}
+
+int Engine::beam_step(const float* logits, const float* scores_in, int32_t* parent, int32_t* token, float* scores_out,
+                      cudaStream_t s) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "beam_step before finalize_weights");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  const int R = cfg_.batch * cfg_.beam;
+  RC(launch_beam_init(bs_, 0, s));
+  FPNMT_CUDA_OK(cudaMemcpyAsync(bs_.score[0], scores_in, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  RC(launch_beam_rowtopk(bs_, logits, cfg_.vocab, s));
+  RC(launch_beam_merge(bs_, s));
+  launches += 3;
+  FPNMT_CUDA_OK(cudaMemcpyAsync(parent, bs_.parent_out, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  FPNMT_CUDA_OK(cudaMemcpyAsync(token, bs_.token_out, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  FPNMT_CUDA_OK(cudaMemcpyAsync(scores_out, bs_.score[1], (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_stop, float* step_scores, cudaStream_t s) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "decode before finalize_weights");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  const int B = cfg_.batch, T = cfg_.max_len;
+  RC(launch_beam_init(bs_, cfg_.true_beam, s));
+  launches += 1;
+  RC(run_program(dec_init_prog_, s));
+  if (cfg_.use_graphs && !step_graph_) RC(capture(step_prog_, &step_graph_));
+  for (int t = 0; t < T; ++t) {
+    RC(launch_prog(step_prog_, step_graph_, s));
+    if (early_stop && (t % 4 == 3) && t + 1 < T) {
+      FPNMT_CUDA_OK(cudaMemcpyAsync(h_pinned_, bs_.n_done, 4, cudaMemcpyDeviceToHost, s));
+      FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+      if (h_pinned_[0] >= B) break;
+    }
+  }
+  const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (out_ids) FPNMT_CUDA_OK(cudaMemcpyAsync(out_ids, bs_.out_ids, (size_t)B * T * 4, kind, s));
+  if (out_len) FPNMT_CUDA_OK(cudaMemcpyAsync(out_len, bs_.out_len, (size_t)B * 4, kind, s));
+  if (step_scores) FPNMT_CUDA_OK(cudaMemcpyAsync(step_scores, step_scores_, (size_t)T * B * 4, cudaMemcpyDeviceToDevice, s));
+  if (on_host) FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int Engine::generate(const float* images, int on_host, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop,
+                     float* step_scores, cudaStream_t s) {
+  RC(encode(images, on_host, nullptr, s, false));
+  return decode(out_ids, out_len, out_on_host, early_stop, step_scores, s);
+}
+
+// --------------------------------------------------------------------------------------------- profiling
+int Engine::profile_program(Program& p, int iters, std::string& json, const char* label) {
+  cudaEvent_t e0, e1;
+  FPNMT_CUDA_OK(cudaEventCreate(&e0));
+  FPNMT_CUDA_OK(cudaEventCreate(&e1));
+  cudaStream_t s = cap_stream_;
+  json += std::string("\"") + label + "\": [";
+  bool first = true;
+  for (auto& op : p) {
+    const int n = op.idempotent ? iters : 1;
+    if (op.idempotent) RC(op.run(s));   // warm
+    FPNMT_CUDA_OK(cudaEventRecord(e0, s));
+    for (int i = 0; i < n; ++i) RC(op.run(s));
+    FPNMT_CUDA_OK(cudaEventRecord(e1, s));
+    FPNMT_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    FPNMT_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s{\"name\": \"%s\", \"kind\": \"%s\", \"us\": %.3f, \"flops\": %.6g, \"bytes\": %.6g}",
+             first ? "" : ", ", op.name.c_str(), op.kind.c_str(), ms * 1000.0 / n, op.flops, op.bytes);
+    json += buf;
+    first = false;
+  }
+  json += "]";
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+int Engine::profile(int iters, char* buf, size_t cap) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "profile before finalize_weights");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  if (iters < 1) iters = 1;
+  // requires a prior encode() so that the image slot points at valid data
+  std::string json = "{";
+  RC(profile_program(enc_prog_, iters, json, "encode"));
+  json += ", ";
+  cudaStream_t s = cap_stream_;
+  RC(launch_beam_init(bs_, cfg_.true_beam, s));
+  RC(run_program(dec_init_prog_, s));
+  const int warm = cfg_.max_len / 2;
+  for (int t = 0; t < warm; ++t) RC(run_program(step_prog_, s));
+  RC(profile_program(dec_init_prog_, iters, json, "decode_init"));
+  json += ", ";
+  RC(profile_program(step_prog_, iters, json, "decode_step"));
+  char tail[128];
+  snprintf(tail, sizeof tail, ", \"decode_step_t\": %d, \"device_bytes\": %zu}", warm, alloc_bytes_);
+  json += tail;
+  FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+  if (cap == 0) return fail(FPNMT_ERR_INVALID, "profile: zero capacity");
+  const size_t n = std::min(cap - 1, json.size());
+  memcpy(buf, json.data(), n);
+  buf[n] = 0;
+  return 0;
+}
+
+}  // namespace fpnmt

@@ -1,0 +1,125 @@
+// Engine: owns weights, activation buffers, the kernel programs (encode / decode step) and their CUDA graphs.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fpnmt.h"
+#include "igemm.cuh"
+#include "kernels.cuh"
+#include "tensormap.cuh"
+
+namespace fpnmt {
+
+struct HostW {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct GemmW {          // device weight matrix [Cout][K] bf16 (split: [Cout][2K]) + fp32 bias
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int Cout = 0, K = 0;
+};
+
+struct Tensor {         // NHWC activation (dense rows: N=1,H=1,W=rows)
+  Act a{nullptr, 0, 0, 0};
+  int N = 0, H = 0, W = 0;
+  size_t pixels() const { return (size_t)N * H * W; }
+};
+
+struct Op {
+  std::string name;
+  std::string kind;     // "igemm", "elementwise", "attention", "beam"
+  std::function<int(cudaStream_t)> run;
+  double flops = 0;     // algorithmic (2*MAC)
+  double bytes = 0;     // algorithmic HBM bytes (inputs read once + outputs written once)
+  bool idempotent = true;
+};
+typedef std::vector<Op> Program;
+
+class Engine {
+ public:
+  Engine(const fpnmt_config& cfg, int device);
+  ~Engine();
+  int init();
+  int set_weight(const char* key, const float* data, const int64_t* shape, int ndim);
+  int finalize();
+  int encode(const float* images, int on_host, float* memory_out, cudaStream_t s, bool cnn_only = false);
+  int features(const float* images, int on_host, float* const out5[5], cudaStream_t s);
+  int get_tap(const char* name, float* out, size_t cap, size_t* count, cudaStream_t s);
+  int decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s);
+  int beam_step(const float* logits, const float* scores_in, int32_t* parent, int32_t* token, float* scores_out,
+                cudaStream_t s);
+  int decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_stop, float* step_scores, cudaStream_t s);
+  int generate(const float* images, int on_host, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop,
+               float* step_scores, cudaStream_t s);
+  int profile(int iters, char* buf, size_t cap);
+  int64_t launches = 0;
+
+ private:
+  fpnmt_config cfg_;
+  int dev_;
+  int num_sms_ = 148;
+  bool split_ = false;
+  bool finalized_ = false;
+  std::unordered_map<std::string, HostW> hw_;
+  std::vector<void*> allocs_;
+  size_t alloc_bytes_ = 0;
+  std::map<std::string, Tensor> taps_;
+
+  // programs
+  Program cnn_prog_, enc_prog_, dec_init_prog_, step_prog_, step_forced_prog_;
+  cudaGraphExec_t cnn_graph_ = nullptr, enc_graph_ = nullptr, step_graph_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
+
+  // buffers referenced at run time
+  const float** img_slot_ = nullptr;      // device slot holding the current image pointer
+  float* img_stage_ = nullptr;            // device staging for host images
+  Tensor feat_[5];                        // head outputs P3..P7
+  Tensor enc_out_;                        // (B*16, 512)
+  int n_base_ = 16;                       // tokens of the baseline view
+  BeamState bs_{};
+  float* logits_ = nullptr;               // [rows][V]
+  int* forced_tokens_ = nullptr;          // [B][T] teacher-forced tokens
+  int* forced_len_ = nullptr;
+  float* forced_logits_ = nullptr;        // [B][T][V]
+  int* h_pinned_ = nullptr;               // pinned scratch for n_done polling
+  float* step_scores_ = nullptr;
+
+  // helpers
+  void* dalloc(size_t bytes);
+  Tensor new_act(int N, int H, int W, int C);
+  Tensor rows_act(int rows, int C) { return new_act(1, 1, rows, C); }
+  static Tensor chan_view(const Tensor& t, int c0, int C);
+  const HostW* W(const std::string& key);
+  int upload_gemm(const std::vector<float>& wt, const std::vector<float>& bias, int Cout, int K, GemmW* out);
+  int prep_conv(const std::string& kernel_key, const std::string& bias_key, const std::string& bn, float eps, GemmW* out,
+                int kpad = 0);
+  int prep_dense_cat(const std::vector<std::string>& names, GemmW* out);       // concat along outputs
+  int prep_dense_stack(const std::vector<std::string>& names, GemmW* out);     // concat along inputs, biases summed
+  int prep_vec(const std::string& key, float** out);
+  int prep_bn_affine(const std::string& bn, float eps, int C, float** scale, float** shift);
+  int prep_depthwise(const std::string& key, const std::string& bn, float eps, float** w, float** bias);
+  int upload_f32(const std::vector<float>& v, float** out);
+
+  int add_conv(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int kh, int kw, int pad_t,
+               int pad_l, int act, int res_mode, const Tensor* res, const Tensor& out, float* out_f32 = nullptr,
+               int ld_f32 = 0);
+  int build_stem_resnet_like(Program& p, const std::string& conv_key, const std::string& bn_key, float eps, Tensor* out);
+  int build_resnet50(Program& p, Tensor c[3]);
+  int build_mobilenetv2(Program& p, Tensor c[3]);
+  int build_densenet121(Program& p, Tensor c[3]);
+  int build_fpn_heads(Program& p, Tensor c[3]);
+  int build_mt_encoder(Program& p);
+  int build_decoder();
+  int run_program(Program& p, cudaStream_t s);
+  int capture(Program& p, cudaGraphExec_t* out);
+  int launch_prog(Program& p, cudaGraphExec_t g, cudaStream_t s);
+  int set_images(const float* images, int on_host, cudaStream_t s);
+  int profile_program(Program& p, int iters, std::string& json, const char* label);
+};
+
+}  // namespace fpnmt

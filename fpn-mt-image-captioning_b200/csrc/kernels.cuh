@@ -1,0 +1,80 @@
+// Launchers for the CUDA-core (bandwidth-bound) kernels of the hot path.
+#pragma once
+#include "common.cuh"
+
+namespace fpnmt {
+
+// ---- elementwise.cu -----------------------------------------------------------------------------
+// fp32 NHWC image (pointer read from a device slot so a captured graph can be re-pointed) -> im2col matrix [N*Ho*Wo][Kpad] for the Cin=3 stem convolutions (k = (ky*kw+kx)*3+c).
+int launch_im2col_stem(const float* const* img_slot, int N, int H, int W, int kh, int kw, int stride, int pad_t, int pad_l, int Ho,
+                       int Wo, Act out, cudaStream_t s);
+// NHWC max-pool k x k / stride, padding handled by ignoring out-of-bounds taps (== -inf padding); with
+// zero_pad the out-of-bounds taps contribute 0 (ZeroPadding2D + valid pool).
+int launch_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, bool zero_pad,
+                   Act out, cudaStream_t s);
+int launch_avgpool2(Act in, int N, int H, int W, Act out, cudaStream_t s);
+int launch_subsample2(Act in, int N, int H, int W, Act out, cudaStream_t s);     // out[n,y,x] = in[n,2y,2x]
+// depthwise 3x3 (+ per-channel bias, ReLU6); w = [9][C] fp32 with BN folded in
+int launch_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int pad_l, int Ho, int Wo, const float* w,
+                        const float* bias, int act, Act out, cudaStream_t s);
+// out = relu(in * scale[c] + shift[c])   (DenseNet pre-activation BN)
+int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const float* shift, Act out, cudaStream_t s);
+// CoAttention_CNN: out[b,p,c] = softmax_p(score[b,:])[p] * cls[b,p,c]
+int launch_coattention(Act score, Act cls, int N, int HW, Act out, cudaStream_t s);
+// Encoder pre-amble: out[b*HW+p] = LN(in[b*HW+p]) + pos[p]   (C = 512)
+int launch_tokens_ln_pos(Act in, int N, int HW, const float* gamma, const float* beta, float eps, const float* pos,
+                         Act out, cudaStream_t s);
+// y = LN(x) over rows of fp32 x[rows][C]
+int launch_layernorm_rows(const float* x, int rows, int C, const float* gamma, const float* beta, float eps, Act out,
+                          cudaStream_t s);
+// Decoder input: out[r] = emb[tok[r]] + pos[*step]
+int launch_embed_pos(const int* tokens, const float* emb, const float* pos, const int* step, int rows, int C, Act out,
+                     cudaStream_t s);
+// fp32 rows -> activation view (used for uploads / tests)
+int launch_f32_to_act(const float* x, size_t rows, int C, Act out, cudaStream_t s);
+int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s);
+
+// ---- attention.cu -------------------------------------------------------------------------------
+// Encoder cross-level attention for one (layer, view): q (B*16 rows) vs K/V of a static view (B*Tk rows).
+int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
+                         int out_col, cudaStream_t s);
+// Decoder self-attention, one new position per row, KV cache with beam-ancestry indirection.
+// qkv: [rows][3*d] (q|k|v) of the new position; caches [rows][T][d]; anc [rows][T] physical row per position.
+int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, const int* step, int rows, int T,
+                              int heads, Act out, cudaStream_t s);
+// Decoder cross-attention over the 16 memory tokens of the row's image.
+int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam, int Tk, int heads, Act out,
+                               cudaStream_t s);
+
+// ---- beam.cu ------------------------------------------------------------------------------------
+struct BeamState {
+  int B, N, V, T;            // images, beam width, vocab, max steps
+  int start_id, end_id;
+  int prob_mode;             // 1: product of probabilities (reference), 0: sum of log-probs
+  float* score[2];           // [B*N] double-buffered beam scores
+  int* seq[2];               // [B*N][T+1] token sequences (seq[.][0] = <start>)
+  int* anc[2];               // [B*N][T] physical cache row per position
+  int* last_tok;             // [B*N] token fed to the next step
+  int* step;                 // device scalar: current step t (0-based)
+  int* done;                 // [B] 1 once the image's top beam has emitted <end>
+  int* n_done;               // [2]: number of finished images, block-completion counter
+  int* out_ids;              // [B][T]
+  int* out_len;              // [B]
+  float* cand_val;           // [B*N][N] per-row candidates (phase 1 -> phase 2)
+  int* cand_idx;             // [B*N][N]
+  float* step_logprob;       // optional [T][B] log-prob (or prob) increment of the chosen top beam, may be null
+  int* parent_out;           // optional [T][B*N] parents chosen per step (debug / parity), may be null
+  int* token_out;            // optional [T][B*N]
+};
+// true_beam = 0 reproduces the reference (all beams start identical, pipeline.py:101-102); 1 starts beams 1..N-1 dead
+int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s);
+// phase 1: per (image, beam) row softmax statistics + candidate scores + row-local top-N
+int launch_beam_rowtopk(const BeamState& st, const float* logits, int ld, cudaStream_t s);
+// phase 2: merge N x N candidates per image, emit parents/tokens/scores, reorder sequences + ancestry,
+// handle <end>, advance the step counter.  Buffers are double-buffered on (step & 1).
+int launch_beam_merge(const BeamState& st, cudaStream_t s);
+// Physical KV reorder variant: dst[row] = src[parent-mapped row] for positions <= step (bandwidth kernel).
+int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
+                     cudaStream_t s);
+
+}  // namespace fpnmt

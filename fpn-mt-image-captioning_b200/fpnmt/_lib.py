@@ -1,0 +1,76 @@
+"""ctypes binding of libfpnmt.so (C ABI declared in include/fpnmt.h).
+
+The library is built in-tree by `build.py` (nvcc, sm_100a).  There is no fallback: if the shared object is
+missing or cannot be loaded this module raises, and every product entry point fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfpnmt.so")
+
+OK, ERR_INVALID, ERR_STATE, ERR_CUDA, ERR_MISSING = 0, 1, 2, 3, 4
+BACKBONE_IDS = {"mobilenet224_1.0": 0, "mobilenetv2": 0, "resnet50": 1, "densenet121": 2}
+PREC_IDS = {"bf16": 0, "bf16x3": 1}
+SCORE_IDS = {"log": 0, "prob": 1}
+
+
+class FpnmtConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "backbone", "image_size", "batch", "beam", "vocab", "max_len", "num_layers", "d_model", "num_heads", "dff",
+        "precision", "score_mode", "start_id", "end_id", "true_beam", "use_graphs")] + [("reserved", C.c_int32 * 8)]
+
+
+class FpnmtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("fpnmt error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/fpnmt.h declares: name -> (restype, argtypes)
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_void_p
+SIGNATURES = {
+    "fpnmt_version": (C.c_char_p, []),
+    "fpnmt_last_error": (C.c_char_p, []),
+    "fpnmt_create": (_i, [C.POINTER(FpnmtConfig), _i, C.POINTER(_vp)]),
+    "fpnmt_destroy": (_i, [_vp]),
+    "fpnmt_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _i]),
+    "fpnmt_finalize_weights": (_i, [_vp]),
+    "fpnmt_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "fpnmt_features": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp]),
+    "fpnmt_get_tap": (_i, [_vp, C.c_char_p, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]),
+    "fpnmt_decode_logits": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "fpnmt_beam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fpnmt_generate": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "fpnmt_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "fpnmt_profile": (_i, [_vp, _i, C.c_char_p, C.c_size_t]),
+    "fpnmt_launch_count": (C.c_int64, [_vp]),
+    "fpnmt_op_conv2d": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libfpnmt.so (once) and attach the prototypes.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libfpnmt.so not found at %s — build it with `python fpn-mt-image-captioning_b200/build.py` "
+            "(or __graft_entry__.build()); there is no CPU / PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise FpnmtError(rc, load().fpnmt_last_error().decode("utf-8", "replace"))

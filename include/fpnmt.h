@@ -1,0 +1,144 @@
+/*
+ * fpnmt.h — C ABI of libfpnmt.so, the B200 (sm_100a) caption-inference engine.
+ *
+ * The reference (samkoesnadi/fpn-MT-image-captioning) is pure Python/TensorFlow and has no FFI; the
+ * boundary this library sits behind is the reference's Python builder API.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repo).  The host-side Python mirror
+ * (fpn-mt-image-captioning_b200/fpnmt) binds these symbols with ctypes; see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only (no C++/torch types); every function returns 0 on success or
+ * an FPNMT_ERR_* code and leaves a message retrievable with fpnmt_last_error(); device pointers are raw
+ * CUDA device addresses (e.g. torch.Tensor.data_ptr() or a DLPack capsule's data field) on the engine's
+ * device; all work is enqueued on the caller's stream (cudaStream_t passed as void*; NULL = default stream);
+ * one handle per GPU; calls on one handle must be serialised by the caller.  There is no CPU fallback.
+ */
+#ifndef FPNMT_H_
+#define FPNMT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FPNMT_API __attribute__((visibility("default")))
+#else
+#define FPNMT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  FPNMT_OK = 0,
+  FPNMT_ERR_INVALID = 1,     /* bad argument / shape / configuration            */
+  FPNMT_ERR_STATE = 2,       /* call order (e.g. encode before finalize)        */
+  FPNMT_ERR_CUDA = 3,        /* CUDA runtime / driver error                     */
+  FPNMT_ERR_MISSING = 4      /* a required weight was never set                 */
+};
+
+enum { FPNMT_BACKBONE_MOBILENETV2 = 0, FPNMT_BACKBONE_RESNET50 = 1, FPNMT_BACKBONE_DENSENET121 = 2 };
+enum { FPNMT_PREC_BF16 = 0,      /* bf16 operands, fp32 accumulate, bf16 activations                          */
+       FPNMT_PREC_BF16X3 = 1 };  /* 3-term split-bf16 products (~fp32 operand precision), fp32 accumulate:
+                                    the parity mode; same kernels, 3x the tensor work                        */
+enum { FPNMT_SCORE_LOG = 0,      /* beam score = sum of log-probs                                             */
+       FPNMT_SCORE_PROB = 1 };   /* beam score = product of softmax probabilities (reference, pipeline.py:117-123) */
+
+typedef struct fpnmt_config {
+  int32_t backbone;      /* FPNMT_BACKBONE_* — models/mobilenet.py:43, models/resnet.py:78, models/densenet.py:73 */
+  int32_t image_size;    /* IMAGE_INPUT_SIZE, common/common_definitions.py:18 (multiple of 256)                  */
+  int32_t batch;         /* images per call (the reference predicts one image at a time, pipeline.py:93)         */
+  int32_t beam;          /* BEAM_SEARCH_N, common/common_definitions.py:22                                       */
+  int32_t vocab;         /* target_vocab_size, utils/pipeline.py:19                                              */
+  int32_t max_len;       /* max_seq_len, utils/pipeline.py:12 / test.py:13                                       */
+  int32_t num_layers;    /* common/common_definitions.py:56                                                      */
+  int32_t d_model;       /* :57 (must be 512)                                                                    */
+  int32_t num_heads;     /* :59 (must be 8)                                                                      */
+  int32_t dff;           /* :58                                                                                  */
+  int32_t precision;     /* FPNMT_PREC_*                                                                         */
+  int32_t score_mode;    /* FPNMT_SCORE_*                                                                        */
+  int32_t start_id;      /* tokenizer.word_index['<start>'], pipeline.py:89                                      */
+  int32_t end_id;        /* tokenizer.word_index['<end>'],   pipeline.py:90                                      */
+  int32_t true_beam;     /* 0 = reference init (all beams identical, pipeline.py:101-102); 1 = only beam 0 alive  */
+  int32_t use_graphs;    /* 1 = replay the encode / decode-step programs as CUDA graphs                          */
+  int32_t reserved[8];
+} fpnmt_config;
+
+typedef struct fpnmt_handle fpnmt_handle;
+
+/* Library / build information ("sm_100a", kernel list).  Never fails. */
+FPNMT_API const char* fpnmt_version(void);
+/* Thread-local message of the last failing call. */
+FPNMT_API const char* fpnmt_last_error(void);
+
+/* Replaces: Transformer(...) / Encoder(...) / FeatureExtractor(...) construction
+ * (models/transformer.py:344-357, :246-264; models/retinanet.py:266-304). */
+FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** out);
+FPNMT_API int fpnmt_destroy(fpnmt_handle* h);
+
+/* Replaces: checkpoint restore / load_weights (utils/pipeline.py:38-48, models/retinanet.py:277-278).
+ * `key` is the variable path of SURVEY.md Appendix B (e.g. "transformer/decoder/dec_layers/0/mha1/wq/kernel");
+ * `data` is HOST float32 in Keras layout (Dense (in,out); Conv2D (kh,kw,Cin,Cout); Depthwise (kh,kw,C,1));
+ * the library copies it. */
+FPNMT_API int fpnmt_set_weight(fpnmt_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+/* Folds BatchNorm, concatenates projections, converts to bf16 (split into hi/lo for BF16X3), uploads, builds
+ * the kernel programs and tensor maps. */
+FPNMT_API int fpnmt_finalize_weights(fpnmt_handle* h);
+
+/* Replaces: Encoder.call(x, training=False, mask=None) (models/transformer.py:266-303).
+ * images: float32 NHWC [batch, S, S, 3] in [-1,1] (dataset.py:19-26), DEVICE pointer unless images_on_host != 0
+ * (then a pinned/pageable HOST pointer; the H2D copy is enqueued on `stream`).
+ * memory_out: optional DEVICE float32 [batch, 16*(S/512)^2.., d_model] = encoder output; may be NULL. */
+FPNMT_API int fpnmt_encode(fpnmt_handle* h, const float* images, int images_on_host, float* memory_out, void* stream);
+
+/* Replaces: FeatureExtractor.call(inp) (models/retinanet.py:306-307).  Runs the CNN part only and copies the five
+ * head outputs (P3..P7 order, NHWC float32, DEVICE pointers, sizes batch*(S/16>>i)^2*d_model) out. */
+FPNMT_API int fpnmt_features(fpnmt_handle* h, const float* images, int images_on_host, float* const out5[5], void* stream);
+
+/* Copies a named intermediate of the last fpnmt_encode (e.g. "C3","C4","C5","P3".."P7","tokens0".."tokens4",
+ * "enc_layer0"..) to a DEVICE float32 buffer of `capacity` floats; writes its element count to *count. */
+FPNMT_API int fpnmt_get_tap(fpnmt_handle* h, const char* name, float* out, size_t capacity, size_t* count, void* stream);
+
+/* Replaces: Transformer.call(inp=enc_output, tar, training=False, look_ahead_mask) (models/transformer.py:359-374)
+ * for teacher-forced parity: memory DEVICE float32 [batch,16,d_model] (NULL = reuse the last fpnmt_encode result),
+ * tokens DEVICE int32 [batch, t]; logits_out DEVICE float32 [batch, t, vocab].  Computed with the KV-cached
+ * step program (position by position), which is mathematically the causal-masked full forward. */
+FPNMT_API int fpnmt_decode_logits(fpnmt_handle* h, const float* memory, const int32_t* tokens, int t, float* logits_out,
+                        void* stream);
+
+/* Replaces: the body of the decode loop, utils/pipeline.py:115-141, on caller-provided logits (the decode-tail
+ * kernels alone): logits DEVICE float32 [batch*beam, vocab], scores_in DEVICE float32 [batch*beam];
+ * outputs DEVICE int32 parent[batch*beam], token[batch*beam], float32 scores_out[batch*beam]. */
+FPNMT_API int fpnmt_beam_step(fpnmt_handle* h, const float* logits, const float* scores_in, int32_t* parent, int32_t* token,
+                    float* scores_out, void* stream);
+
+/* Replaces: Pipeline.predict (utils/pipeline.py:82-154) for a batch: encoder + beam-search decode.
+ * out_ids DEVICE-or-HOST int32 [batch, max_len] (0 padded), out_len int32 [batch]: exactly what predict() returns
+ * per image (<start> stripped, trailing <end> stripped).  outputs_on_host != 0: results are copied to host and
+ * the call synchronises the stream.  early_stop != 0: stop when every image's top beam has emitted <end>
+ * (pipeline.py:147); 0: always run max_len steps (throughput runs).
+ * step_scores: optional DEVICE float32 [max_len, batch] score of the top beam after each step (may be NULL). */
+FPNMT_API int fpnmt_generate(fpnmt_handle* h, const float* images, int images_on_host, int32_t* out_ids, int32_t* out_len,
+                   int outputs_on_host, int early_stop, float* step_scores, void* stream);
+/* Same, from an encoder output already in the engine (after fpnmt_encode) — the decode half only. */
+FPNMT_API int fpnmt_decode(fpnmt_handle* h, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop,
+                 float* step_scores, void* stream);
+
+/* Per-kernel timing of the encode and decode-step programs (CUDA events, `iters` repetitions each).  Writes a JSON
+ * document into buf (NUL terminated, truncated to cap).  Reports algorithmic FLOPs/bytes per kernel. */
+FPNMT_API int fpnmt_profile(fpnmt_handle* h, int iters, char* buf, size_t cap);
+/* Number of kernel launches issued by this handle since creation (graph replays count their kernel nodes). */
+FPNMT_API int64_t fpnmt_launch_count(fpnmt_handle* h);
+
+/* ---- stand-alone operators (used by the parity tests to check single kernels) ------------------------------- */
+/* out[pix, co] = act(conv(x) + bias [+ residual]); x DEVICE float32 NHWC [N,H,W,Cin]; kernel HOST float32
+ * (kh,kw,Cin,Cout); bias HOST float32 [Cout] or NULL; residual DEVICE float32 (same shape as out, or
+ * [N,H/2,W/2,Cout] when res_mode == 2) or NULL; out DEVICE float32 [N,H,W,Cout].  stride 1, zero padding
+ * (pad_top, pad_left; the rest implied by the output size == input size). act: 0 none,1 relu,2 leaky(0.2),3 relu6 */
+FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, int H, int W, int Cin, const float* kernel,
+                    int kh, int kw, int Cout, int pad_top, int pad_left, const float* bias, int act,
+                    const float* residual, int res_mode, float* out, int force_bn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPNMT_H_ */
