@@ -1,0 +1,200 @@
+"""CPU tests of the host side: the C ABI library loads and exports every symbol include/fpnmt.h declares,
+the variable tree, the data formats either side of the path, multi-process sharding (gloo, world_size 2),
+and that the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "fpnmt.h")).read()
+    declared = sorted(set(re.findall(r"FPNMT_API\s+[\w\s\*]+?\b(fpnmt_\w+)\s*\(", hdr)))
+    assert len(declared) >= 16
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), "libfpnmt.so does not export %s" % name
+    from fpnmt import _lib
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes prototypes and header out of sync"
+
+
+def test_library_has_blackwell_code(built_lib):
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "sm_100" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):           # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnemonic in sass, "expected %s in the SASS of libfpnmt.so" % mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")          # no legacy mma.sync path
+
+
+def test_no_gpu_fails_loudly(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fpnmt import _lib
+    lib = _lib.load()
+    cfg, h = _lib.FpnmtConfig(), C.c_void_p()
+    rc = lib.fpnmt_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == _lib.ERR_CUDA and b"no CPU fallback" in lib.fpnmt_last_error()
+    from fpnmt.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine({}, batch=1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fpn-mt-image-captioning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "fpnmt_oracle" not in src and "oracle/" not in src, f
+
+
+def test_config_mirrors_reference_constants():
+    from fpnmt import config as cfg
+    assert (cfg.num_layers, cfg.d_model, cfg.dff, cfg.num_heads) == (6, 512, 2048, 8)
+    assert (cfg.IMAGE_INPUT_SIZE, cfg.BEAM_SEARCH_N, cfg.TOP_K) == (512, 4, 10000)
+    assert (cfg.NUM_OF_PYRAMIDS, cfg.BASELINE_INDEX, cfg.N_CONV_SUBMODULE, cfg.NUM_OF_RETINANET_FILTERS) == (5, 3, 2, 256)
+
+
+@pytest.mark.parametrize("backbone,nparams", [("mobilenet224_1.0", None), ("resnet50", None), ("densenet121", None)])
+def test_variable_tree(backbone, nparams):
+    from fpnmt.weights import model_spec, BACKBONE_TAPS
+    spec = model_spec(backbone, vocab=10000)
+    keys = [k for k, _, _ in spec]
+    assert len(keys) == len(set(keys))
+    d = dict((k, s) for k, s, _ in spec)
+    assert d["transformer/encoder/enc_layers/5/mhas/3/wq/kernel"] == (512, 512)
+    assert d["transformer/decoder/dec_layers/0/mha2/dense/bias"] == (512,)
+    assert d["transformer/decoder/embedding/embeddings"] == (10000, 512)
+    assert d["transformer/final_layer/kernel"] == (512, 10000)
+    assert d["transformer/encoder/feature_extractor/model/conv2d_2/kernel"] == (3, 3, 256, 1)
+    assert d["transformer/encoder/feature_extractor/model/conv2d_5/kernel"] == (3, 3, 256, 512)
+    c5 = BACKBONE_TAPS[backbone][2]
+    assert d["transformer/encoder/feature_extractor/retinanet_model/C5_reduced/kernel"] == (1, 1, c5, 256)
+
+
+def test_init_weights_distributions_and_roundtrip(tmp_path):
+    from fpnmt.weights import init_weights, load_weights, save_weights
+    w = init_weights("mobilenet224_1.0", vocab=64, num_layers=1, seed=3)
+    k = w["transformer/encoder/enc_layers/0/ffn1/kernel"]                      # he_normal, fan_in 512
+    assert abs(k.std() - np.sqrt(2 / 512)) < 0.003 and np.abs(k).max() <= 2 * np.sqrt(2 / 512) / 0.8796 + 1e-6
+    r = w["transformer/encoder/feature_extractor/retinanet_model/regression_submodel/pyramid_regression_0/kernel"]
+    assert abs(r.std() - 0.01) < 5e-4
+    e = w["transformer/decoder/embedding/embeddings"]
+    assert e.min() >= -0.05 and e.max() <= 0.05
+    assert (w["transformer/final_layer/bias"] == 0).all()
+    p = str(tmp_path / "w.npz")
+    save_weights(p, w)
+    w2 = load_weights(p)
+    assert set(w2) == set(w) and all((w2[k] == w[k]).all() for k in w)
+    w3 = init_weights("mobilenet224_1.0", vocab=64, num_layers=1, seed=3)
+    assert all((w3[k] == w[k]).all() for k in w)                                # deterministic
+
+
+def test_tokenizer_roundtrip_double_encoded_json(tmp_path):
+    from fpnmt.dataset import Tokenizer, load_tokenizer_from_path, store_tokenizer_to_path
+    tok = Tokenizer.synthetic(40)
+    p = str(tmp_path / "_tokenizer.json")
+    store_tokenizer_to_path(tok, p)
+    assert isinstance(json.load(open(p)), str)                 # json.dumps(tokenizer.to_json()) — dataset.py:143-146
+    t2 = load_tokenizer_from_path(p)
+    assert t2.word_index == tok.word_index and t2.index_word == tok.index_word
+    assert t2.word_index["<start>"] == 2 and t2.word_index["<end>"] == 3 and len(t2.index_word) == 40
+    assert t2.sequences_to_texts([[5, 6, 0, 7]]) == ["w5 w6 <pad> w7"]
+    assert t2.sequences_to_texts([[5, 999]]) == ["w5"]         # unknown indices are skipped like Keras
+
+
+def test_load_image_contract(tmp_path):
+    from PIL import Image
+    from fpnmt.dataset import load_image, resize_bilinear_tf2
+    rng = np.random.default_rng(0)
+    arr = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    p = str(tmp_path / "a.png")
+    Image.fromarray(arr).save(p)
+    img, cap = load_image(p, "x")
+    assert img.shape == (512, 512, 3) and img.dtype == np.float32 and cap == "x"
+    assert img.min() >= -1.0 and img.max() <= 1.0
+    # identity resize and exact 2x checks of the half-pixel bilinear kernel
+    a = rng.random((4, 4, 1)).astype(np.float32)
+    assert np.allclose(resize_bilinear_tf2(a, 4, 4), a)
+    up = resize_bilinear_tf2(a, 8, 8)
+    assert np.allclose(up[0, 0], a[0, 0]) and np.allclose(up[1, 1, 0], (9 * a[0, 0, 0] + 3 * a[0, 1, 0] + 3 * a[1, 0, 0] + a[1, 1, 0]) / 16)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(a).permute(2, 0, 1)[None], size=(7, 5), mode="bilinear",
+                                          align_corners=False, antialias=False)[0].permute(1, 2, 0).numpy()
+    assert np.allclose(resize_bilinear_tf2(a, 7, 5), ref, atol=1e-6)
+
+
+def test_builder_signatures_match_reference():
+    import inspect
+    from fpnmt import retinanet as R
+    from fpnmt.pipeline import Pipeline
+    from fpnmt.transformer import Transformer
+    assert list(inspect.signature(Pipeline.__init__).parameters)[:4] == ["self", "tokenizer_filename", "checkpoint_path", "max_seq_len"]
+    assert list(inspect.signature(Pipeline.predict).parameters) == ["self", "img", "max_seq_len", "plot_layer"]
+    assert list(inspect.signature(Transformer.__init__).parameters)[:10] == [
+        "self", "num_layers", "d_model", "num_heads", "dff", "input_vocab_size", "target_vocab_size", "rate", "max_position", "max_seq_len"]
+    assert list(inspect.signature(R.retinanet).parameters)[:7] == [
+        "inputs", "backbone_layers", "num_classes", "num_anchors", "create_pyramid_features", "submodels", "name"]
+    assert list(inspect.signature(R.mobilenet_retinanet).parameters)[:4] == ["num_classes", "backbone", "inputs", "modifier"]
+    assert R.mobilenet_retinanet(80).backbone_layers == ("block_5_add", "block_12_add", "out_relu")
+    assert R.backbone("resnet50").retinanet(80).backbone == "resnet50"
+    assert R.densenet_retinanet(80).backbone_layers[2] == "conv5_block16_concat"
+    with pytest.raises(ValueError):
+        R.resnet_retinanet(80, backbone="resnet18")
+    with pytest.raises(NotImplementedError):
+        R.backbone("vgg16")
+
+
+def test_shard_bounds_cover_and_balance():
+    from fpnmt.dist import shard_bounds
+    for total in (0, 1, 7, 64, 100):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "fpn-mt-image-captioning_b200"))
+import torch
+from fpnmt import dist as fd
+rank, local, world = fd.init_from_env("gloo")
+b, t = 3, 5
+ids = (torch.arange(b * t, dtype=torch.int32).reshape(b, t) + 100 * rank)
+lens = torch.full((b,), rank + 1, dtype=torch.int32)
+allids, alllens = fd.allgather_captions(ids, lens, world)
+assert allids.shape == (world * b, t) and alllens.shape == (world * b,)
+for r in range(world):
+    assert (allids[r * b:(r + 1) * b] == torch.arange(b * t, dtype=torch.int32).reshape(b, t) + 100 * r).all()
+    assert (alllens[r * b:(r + 1) * b] == r + 1).all()
+assert fd.max_over_ranks(float(rank)) == world - 1
+lo, hi = fd.shard_bounds(10, rank, world)
+print("rank", rank, "ok", lo, hi)
+'''
+
+
+def test_allgather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                       capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok 0 5" in r.stdout and "rank 1 ok 5 10" in r.stdout
+
+
+def test_bench_reference_arm_line_shape():
+    import bench
+    assert bench.WORKLOADS["c2"]["backbone"] == "resnet50" and bench.WORKLOADS["c2"]["batch"] == 64
+    p = bench.measured_peaks()
+    assert p["hbm_gbs"] > 1000 and p["tf"] > 100
