@@ -65,24 +65,26 @@ class ClockSampler:
         self.idx, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self.stop_flag = threading.Event()
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
+        self.proc = True
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        cmd = ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"]
+        while not self.stop_flag.is_set():
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=5)
+                self.lines.extend(l.strip() for l in r.stdout.splitlines() if l.strip())
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
+        self.stop_flag.set()
+        self.t.join(timeout=6)
         sm, smax, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -221,7 +223,7 @@ def run_own(args, wl):
     value = total_images / (ms * 1e-3)
     e2e_value = total_images / (ms_e2e * 1e-3)
     # ---- roofline of the dominant kernel, measured live with the engine's per-op CUDA-event profiler
-    prof = eng.profile(iters=3)
+    prof = eng.profile(iters=args.profile_iters)
     if args.profile_out:
         with open(args.profile_out, "w") as f:
             json.dump(prof, f, indent=1)
@@ -273,6 +275,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-iters", type=int, default=10)
     ap.add_argument("--profile-out", default=None, help="write the engine's per-op profile (JSON) here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -1,4 +1,5 @@
 // extern "C" surface of libfpnmt.so (see include/fpnmt.h).
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -9,6 +10,13 @@
 namespace fpnmt {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FPNMT_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace fpnmt
 
 using namespace fpnmt;
@@ -169,7 +177,8 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
   bf16* dw = (bf16*)dal(hw.size() * 2);
   float* dbias = nullptr;
   if (bias) {
-    dbias = (float*)dal((size_t)(Cout + 8) * 4);
+    dbias = (float*)dal((size_t)(Cout + 32) * 4);
+    cudaMemsetAsync(dbias, 0, (size_t)(Cout + 32) * 4, s);
     cudaMemcpyAsync(dbias, bias, (size_t)Cout * 4, cudaMemcpyHostToDevice, s);
   }
   cudaMemcpyAsync(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice, s);

@@ -42,6 +42,8 @@ __device__ __forceinline__ void ld_row64(const Act& a, size_t row, int col, floa
 // for the score pass and own 2 output dims for the value pass.
 __global__ void __launch_bounds__(128) k_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int Tq, int Tk,
                                                        Act out, int out_col) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float sq[16][DH];
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,30 +111,54 @@ int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, 
     return 1;
   }
   dim3 grid(B, heads);
-  k_enc_attention<<<grid, 128, 0, s>>>(q, q_col, kv, k_col, v_col, Tq, Tk, out, out_col);
+  FPNMT_CUDA_OK(launch_k(k_enc_attention, dim3(grid), dim3(128), 0, s, q, q_col, kv, k_col, v_col, Tq, Tk, out, out_col));
   LAUNCH_CHECK();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------- decoder attention
-// Warp-level attention of ONE query over Tk cached positions.  Score pass: lane j owns position k0+j and reads
-// its 128 B key row (independent loads -> memory-level parallelism); value pass: lanes own 2 output dims and the
-// probabilities are broadcast by shuffle.  `krow(pos)` maps a position to the row of the K/V views.
+// Warp-level attention of ONE query over Tk cached positions.  The query (pre-scaled) lives in shared memory
+// (broadcast reads).  Score pass: lane j owns position k0+j and reads its 128 B key row with 8 independent 16 B
+// loads (memory-level parallelism, few registers); value pass: lanes own 2 output dims and the probabilities are
+// broadcast by shuffle, loads unrolled.  `krow(pos)` maps a position to the row of the K/V views.
+__device__ __forceinline__ float dot_row64(const Act& a, size_t row, int col, const float* __restrict__ qs) {
+  const bf16* p = a.p + row * (size_t)a.ld + col;
+  uint4 h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const uint4*>(p + i * 8);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float f[8];
+    unpack8(h[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(qs[i * 8 + j], f[j], acc);
+  }
+  if (a.lo) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const uint4*>(p + a.lo + i * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float f[8];
+      unpack8(h[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(qs[i * 8 + j], f[j], acc);
+    }
+  }
+  return acc;
+}
+
 template <typename RowFn>
-__device__ __forceinline__ void warp_attend(const float* qf, const Act& kc, int k_col, const Act& vc, int v_col, int Tk,
-                                            RowFn krow, int lane, float& m, float& l, float& o0, float& o1) {
+__device__ __forceinline__ void warp_attend(const float* __restrict__ qs, const Act& kc, int k_col, const Act& vc,
+                                            int v_col, int Tk, RowFn krow, int lane, float& m, float& l, float& o0,
+                                            float& o1) {
   for (int k0 = 0; k0 < Tk; k0 += 32) {
     const int pos = k0 + lane;
     float sc = -INFINITY;
-    size_t myrow = 0;
+    unsigned myrow = 0;
     if (pos < Tk) {
-      myrow = krow(pos);
-      float kr[DH];
-      ld_row64(kc, myrow, k_col, kr);
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) a = fmaf(qf[d], kr[d], a);
-      sc = a;
+      myrow = (unsigned)krow(pos);
+      sc = dot_row64(kc, myrow, k_col, qs);
     }
     const float mn = fmaxf(m, warp_max(sc));
     const float corr = __expf(m - mn);
@@ -142,9 +168,9 @@ __device__ __forceinline__ void warp_attend(const float* qf, const Act& kc, int 
     o1 *= corr;
     m = mn;
     const int kmax = min(32, Tk - k0);
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < kmax; ++j) {
-      const size_t r = __shfl_sync(0xffffffffu, (unsigned long long)myrow, j);
+      const unsigned r = __shfl_sync(0xffffffffu, myrow, j);
       const float pj = __shfl_sync(0xffffffffu, p, j);
       const float2 v = ld_pair(vc, r, v_col, lane);
       o0 = fmaf(pj, v.x, o0);
@@ -153,30 +179,35 @@ __device__ __forceinline__ void warp_attend(const float* qf, const Act& kc, int 
   }
 }
 
+constexpr int DEC_WARPS = 4;
+
 // one warp per (row, head).  Position t = *step is the new token: its K/V come from `qkv` and are appended to the
 // cache at [row][t]; positions t' < t are read from cache row anc[row][t'] (the beam's ancestor at that time).
-__global__ void __launch_bounds__(256) k_dec_self_attention(Act qkv, Act kc, Act vc, const int* __restrict__ anc_base,
-                                                            size_t anc_stride, const int* __restrict__ step, int rows,
-                                                            int T, int heads, Act out) {
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_self_attention(Act qkv, Act kc, Act vc,
+                                                                       const int* __restrict__ anc_base, size_t anc_stride,
+                                                                       const int* __restrict__ step, int rows, int T,
+                                                                       int heads, Act out) {
+  __shared__ float sq[DEC_WARPS][DH];
+  pdl_launch();
+  pdl_wait();
+  const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = gw / heads, h = gw % heads;
   const int d = heads * DH;
   const int t = *step;
   const int* anc = anc_base + (size_t)(t & 1) * anc_stride + (size_t)row * T;
+  const float2 qv = ld_pair(qkv, row, h * DH, lane);
   const float2 kn = ld_pair(qkv, row, d + h * DH, lane);
   const float2 vn = ld_pair(qkv, row, 2 * d + h * DH, lane);
+  sq[w][lane * 2] = qv.x * 0.125f;       // 1/sqrt(64)
+  sq[w][lane * 2 + 1] = qv.y * 0.125f;
   st_pair(kc, (size_t)row * T + t, h * DH, lane, kn.x, kn.y);     // append the new K/V to the cache
   st_pair(vc, (size_t)row * T + t, h * DH, lane, vn.x, vn.y);
-  float qf[DH];
-  ld_row64(qkv, row, h * DH, qf);
-#pragma unroll
-  for (int i = 0; i < DH; ++i) qf[i] *= 0.125f;
+  __syncwarp();
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  warp_attend(qf, kc, h * DH, vc, h * DH, t, [&](int pos) { return (size_t)anc[pos] * T + pos; }, lane, m, l, o0, o1);
+  warp_attend(sq[w], kc, h * DH, vc, h * DH, t, [&](int pos) { return (size_t)anc[pos] * T + pos; }, lane, m, l, o0, o1);
   {   // the new position itself (K/V still in registers)
-    const float2 qv = ld_pair(qkv, row, h * DH, lane);
     const float sc = warp_sum((qv.x * kn.x + qv.y * kn.y) * 0.125f);
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn);
@@ -191,34 +222,36 @@ __global__ void __launch_bounds__(256) k_dec_self_attention(Act qkv, Act kc, Act
 int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, const int* step, int rows, int T,
                               int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
-  k_dec_self_attention<<<(warps + 7) / 8, 256, 0, s>>>(qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads,
-                                                        out);
-  LAUNCH_CHECK();
+  FPNMT_CUDA_OK(launch_k(k_dec_self_attention, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                         qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
   return 0;
 }
 
-__global__ void __launch_bounds__(256) k_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam,
-                                                             int Tk, int heads, Act out) {
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows,
+                                                                        int beam, int Tk, int heads, Act out) {
+  __shared__ float sq[DEC_WARPS][DH];
+  pdl_launch();
+  pdl_wait();
+  const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = gw / heads, h = gw % heads;
   const int img = row / beam;
-  float qf[DH];
-  ld_row64(q, row, h * DH, qf);
-#pragma unroll
-  for (int i = 0; i < DH; ++i) qf[i] *= 0.125f;
+  const float2 qv = ld_pair(q, row, h * DH, lane);
+  sq[w][lane * 2] = qv.x * 0.125f;
+  sq[w][lane * 2 + 1] = qv.y * 0.125f;
+  __syncwarp();
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  warp_attend(qf, kv, k_col + h * DH, kv, v_col + h * DH, Tk, [&](int pos) { return (size_t)img * Tk + pos; }, lane, m,
-              l, o0, o1);
+  warp_attend(sq[w], kv, k_col + h * DH, kv, v_col + h * DH, Tk, [&](int pos) { return (size_t)img * Tk + pos; }, lane,
+              m, l, o0, o1);
   const float inv = 1.f / l;
   st_pair(out, row, h * DH, lane, o0 * inv, o1 * inv);
 }
 int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam, int Tk, int heads, Act out,
                                cudaStream_t s) {
   const int warps = rows * heads;
-  k_dec_cross_attention<<<(warps + 7) / 8, 256, 0, s>>>(q, kv, k_col, v_col, rows, beam, Tk, heads, out);
-  LAUNCH_CHECK();
+  FPNMT_CUDA_OK(launch_k(k_dec_cross_attention, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                         q, kv, k_col, v_col, rows, beam, Tk, heads, out));
   return 0;
 }
 

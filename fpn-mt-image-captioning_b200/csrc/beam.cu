@@ -17,6 +17,8 @@ namespace fpnmt {
 constexpr int RT_MAXV4 = 12;   // float4 loads per thread -> V <= 48 * blockDim
 
 __global__ void k_beam_init(BeamState st, int true_beam) {
+  pdl_launch();
+  pdl_wait();
   const int rows = st.B * st.N;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
@@ -40,8 +42,7 @@ __global__ void k_beam_init(BeamState st, int true_beam) {
 }
 int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s) {
   const int rows = st.B * st.N;
-  k_beam_init<<<(rows + 255) / 256, 256, 0, s>>>(st, true_beam);
-  LAUNCH_CHECK();
+  FPNMT_CUDA_OK(launch_k(k_beam_init, dim3((rows + 255) / 256), dim3(256), 0, s, st, true_beam));
   return 0;
 }
 
@@ -60,14 +61,18 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// Phase 1.  One block per (image, beam) row.  Row statistics with one block reduction each; then every WARP extracts
+// its own top-N with shuffle-only arg-max rounds (no block barrier), and warp 0 merges the NW*N survivors.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const float* __restrict__ logits, int ld) {
-  __shared__ float s_f[32];
-  __shared__ int s_i[32];
-  __shared__ float s_bc;
-  __shared__ int s_bi;
+  constexpr int NW = THREADS / 32;
+  __shared__ float s_red[NW];
+  __shared__ float s_cv[NW * 32];
+  __shared__ int s_ci[NW * 32];
+  pdl_launch();
+  pdl_wait();
   const int row = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = st.V, N = st.N;
   const int t = *st.step;
   const float score = st.score[t & 1][row];
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
   float v[RT_MAXV4 * 4];
 #pragma unroll
   for (int i = 0; i < RT_MAXV4; ++i) {
-    const int e = (i * blockDim.x + tid) * 4;
+    const int e = (i * THREADS + tid) * 4;
     if (e + 3 < V) {
       const float4 q = *reinterpret_cast<const float4*>(x + e);
       v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
@@ -90,37 +95,28 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
 #pragma unroll
   for (int i = 0; i < RT_MAXV4 * 4; ++i) m = fmaxf(m, v[i]);
   m = warp_max(m);
-  if (lane == 0) s_f[warp] = m;
+  if (lane == 0) s_red[warp] = m;
   __syncthreads();
-  if (warp == 0) {
-    float q = lane < nw ? s_f[lane] : -INFINITY;
-    q = warp_max(q);
-    if (lane == 0) s_bc = q;
-  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w) m = fmaxf(m, s_red[w]);
   __syncthreads();
-  m = s_bc;
   // sum exp
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < RT_MAXV4 * 4; ++i) sum += expf(v[i] - m);   // exp(-inf) = 0 for the padding
   sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
   __syncthreads();
-  if (lane == 0) s_f[warp] = sum;
-  __syncthreads();
-  if (warp == 0) {
-    float q = lane < nw ? s_f[lane] : 0.f;
-    q = warp_sum(q);
-    if (lane == 0) s_bc = q;
-  }
-  __syncthreads();
-  sum = s_bc;
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) sum += s_red[w];
   // candidate scores
   if (st.prob_mode) {
 #pragma unroll
     for (int i = 0; i < RT_MAXV4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int e = (i * blockDim.x + tid) * 4 + j;
+        const int e = (i * THREADS + tid) * 4 + j;
         v[4 * i + j] = (e < V) ? (expf(v[4 * i + j] - m) / sum) * score : -INFINITY;   // pipeline.py:117,122
       }
   } else {
@@ -129,11 +125,11 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
     for (int i = 0; i < RT_MAXV4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int e = (i * blockDim.x + tid) * 4 + j;
+        const int e = (i * THREADS + tid) * 4 + j;
         v[4 * i + j] = (e < V) ? score + (v[4 * i + j] - lse) : -INFINITY;
       }
   }
-  // N rounds of block-wide arg-max with exclusion
+  // warp-local top-N: N shuffle-only rounds
   unsigned long long taken = 0ull;
   for (int k = 0; k < N; ++k) {
     float bv = -INFINITY;
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
     for (int i = 0; i < RT_MAXV4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int e = (i * blockDim.x + tid) * 4 + j;
+        const int e = (i * THREADS + tid) * 4 + j;
         const bool free_slot = !((taken >> (4 * i + j)) & 1ull) && e < V;
         if (free_slot && better(v[4 * i + j], e, bv, bi)) {
           bv = v[4 * i + j];
@@ -150,28 +146,43 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
         }
       }
     warp_argmax(bv, bi);
-    __syncthreads();
     if (lane == 0) {
-      s_f[warp] = bv;
-      s_i[warp] = bi;
+      s_cv[warp * 32 + k] = bv;
+      s_ci[warp * 32 + k] = bi;
     }
-    __syncthreads();
-    if (warp == 0) {
-      float qv = lane < nw ? s_f[lane] : -INFINITY;
-      int qi = lane < nw ? s_i[lane] : 0x7fffffff;
-      warp_argmax(qv, qi);
+    if (bi != 0x7fffffff) {
+      const int slot4 = bi >> 2;                        // which float4 of the row
+      if (slot4 % THREADS == tid) taken |= 1ull << (4 * (slot4 / THREADS) + (bi & 3));
+    }
+  }
+  __syncthreads();
+  // warp 0 merges the NW*N survivors (lane holds up to NW of them; N <= 32)
+  if (warp == 0) {
+    float cv[NW];
+    int ci[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const bool ok = lane < N;
+      cv[w] = ok ? s_cv[w * 32 + lane] : -INFINITY;
+      ci[w] = ok ? s_ci[w * 32 + lane] : 0x7fffffff;
+    }
+    for (int k = 0; k < N; ++k) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+        if (ci[w] != 0x7fffffff && better(cv[w], ci[w], bv, bi)) {
+          bv = cv[w];
+          bi = ci[w];
+        }
+      warp_argmax(bv, bi);
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+        if (ci[w] == bi) ci[w] = 0x7fffffff;            // indices are unique within a row -> exactly one owner
       if (lane == 0) {
-        s_bc = qv;
-        s_bi = qi;
-        st.cand_val[(size_t)row * N + k] = qv;
-        st.cand_idx[(size_t)row * N + k] = qi;
+        st.cand_val[(size_t)row * N + k] = bv;
+        st.cand_idx[(size_t)row * N + k] = bi;
       }
-    }
-    __syncthreads();
-    const int win = s_bi;
-    if (win != 0x7fffffff) {
-      const int slot4 = win >> 2;                       // which float4 of the row
-      if (slot4 % (int)blockDim.x == tid) taken |= 1ull << (4 * (slot4 / (int)blockDim.x) + (win & 3));
     }
   }
 }
@@ -185,63 +196,81 @@ int launch_beam_rowtopk(const BeamState& st, const float* logits, int ld, cudaSt
     return 1;
   }
   if (256 * RT_MAXV4 * 4 >= st.V)
-    k_beam_rowtopk<256><<<st.B * st.N, 256, 0, s>>>(st, logits, ld);
+    FPNMT_CUDA_OK(launch_k(k_beam_rowtopk<256>, dim3(st.B * st.N), dim3(256), 0, s, st, logits, ld));
   else
-    k_beam_rowtopk<512><<<st.B * st.N, 512, 0, s>>>(st, logits, ld);
-  LAUNCH_CHECK();
+    FPNMT_CUDA_OK(launch_k(k_beam_rowtopk<512>, dim3(st.B * st.N), dim3(512), 0, s, st, logits, ld));
   return 0;
 }
 
-// one warp per image
-__global__ void __launch_bounds__(32) k_beam_merge(BeamState st) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+// Phase 2.  One block per image: warp 0 selects the N best of the N x N candidates (registers + shuffles), all warps
+// then copy the parent sequences / ancestry rows.
+constexpr int MERGE_WARPS = 8;
+__global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
+  __shared__ int s_parent[32], s_token[32];
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = st.N, V = st.V, T = st.T;
   const int t = *st.step;
   const int cur = t & 1, nxt = cur ^ 1;
   const int NN = N * N;
-  // each lane holds candidates lane, lane+32, ...  (N <= 32 -> at most 32 per lane)
-  unsigned taken = 0u;
-  int my_parent = 0, my_token = 0;
-  float my_score = 0.f;
-  for (int k = 0; k < N; ++k) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    int bslot = -1;
-    for (int c = lane, s = 0; c < NN; c += 32, ++s) {
-      if ((taken >> s) & 1u) continue;
-      const int n = c / N;
-      const float val = st.cand_val[(size_t)(b * N) * N + c];
-      const int tok = st.cand_idx[(size_t)(b * N) * N + c];
-      if (tok == 0x7fffffff) continue;
-      const int flat = n * V + tok;
-      if (bslot < 0 || better(val, flat, bv, bi)) {
-        bv = val;
-        bi = flat;
-        bslot = s;
+  const int rows0 = b * N;
+  if (warp == 0) {
+    // lane holds candidates lane, lane+32, ... (at most 32 for N <= 32)
+    float cv[32];
+    int cf[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      const int c = lane + 32 * s;
+      cv[s] = -INFINITY;
+      cf[s] = 0x7fffffff;
+      if (c < NN) {
+        const int tok = st.cand_idx[(size_t)rows0 * N + c];
+        if (tok != 0x7fffffff) {
+          cv[s] = st.cand_val[(size_t)rows0 * N + c];
+          cf[s] = (c / N) * V + tok;                               // flat index over the N x V candidates
+        }
+      }
+      if (32 * (s + 1) >= NN) break;
+    }
+    int my_parent = 0, my_token = 0;
+    float my_score = 0.f;
+    for (int k = 0; k < N; ++k) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        if (cf[s] != 0x7fffffff && better(cv[s], cf[s], bv, bi)) {
+          bv = cv[s];
+          bi = cf[s];
+        }
+        if (32 * (s + 1) >= NN) break;
+      }
+      warp_argmax(bv, bi);
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        if (cf[s] == bi) cf[s] = 0x7fffffff;
+        if (32 * (s + 1) >= NN) break;
+      }
+      if (lane == k) {
+        my_parent = bi / V;                                          // pipeline.py:130
+        my_token = bi - my_parent * V;                               // pipeline.py:131
+        my_score = bv;
       }
     }
-    float wv = bv;
-    int wi = bi;
-    warp_argmax(wv, wi);
-    if (bslot >= 0 && wi == bi && wv == bv) taken |= 1u << bslot;    // flat indices are unique -> one owner
-    if (lane == k) {
-      my_parent = wi / V;                                            // pipeline.py:130
-      my_token = wi - my_parent * V;                                 // pipeline.py:131
-      my_score = wv;
+    if (lane < N) {                                                  // lanes 0..N-1 hold the new beams in rank order
+      s_parent[lane] = my_parent;
+      s_token[lane] = my_token;
+      st.score[nxt][rows0 + lane] = my_score;
+      st.last_tok[rows0 + lane] = my_token;
+      if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + lane] = my_parent;
+      if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + lane] = my_token;
     }
+    if (lane == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = my_score;
   }
-  // lanes 0..N-1 now hold the new beams in rank order
-  const int rows0 = b * N;
-  if (lane < N) {
-    st.score[nxt][rows0 + lane] = my_score;
-    st.last_tok[rows0 + lane] = my_token;
-    if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + lane] = my_parent;
-    if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + lane] = my_token;
-  }
-  if (lane == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = my_score;
-  for (int n = 0; n < N; ++n) {
-    const int par = __shfl_sync(0xffffffffu, my_parent, n);
-    const int tok = __shfl_sync(0xffffffffu, my_token, n);
+  __syncthreads();
+  for (int n = warp; n < N; n += MERGE_WARPS) {
+    const int par = s_parent[n], tok = s_token[n];
     const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
     int* dseq = st.seq[nxt] + (size_t)(rows0 + n) * (T + 1);
     for (int j = lane; j <= t; j += 32) dseq[j] = sseq[j];            // pipeline.py:134-137
@@ -253,39 +282,42 @@ __global__ void __launch_bounds__(32) k_beam_merge(BeamState st) {
       danc[t] = rows0 + par;
     }
   }
-  __syncwarp();
+  __syncthreads();
   // top beam is rank 0 (scores are sorted; tf.argmax returns the first maximum) — pipeline.py:143-148
-  const int top_tok = __shfl_sync(0xffffffffu, my_token, 0);
-  if (!st.done[b] && (top_tok == st.end_id || t == T - 1)) {
-    const int* res = st.seq[nxt] + (size_t)rows0 * (T + 1);
-    const int len = (top_tok == st.end_id) ? t : t + 1;               // strip <start> and a trailing <end>
-    for (int j = lane; j < len; j += 32) st.out_ids[(size_t)b * T + j] = res[1 + j];
-    __syncwarp();
-    if (lane == 0) {
-      st.out_len[b] = len;
-      st.done[b] = 1;
-      atomicAdd(st.n_done, 1);
+  if (warp == 0) {
+    const int top_tok = s_token[0];
+    if (!st.done[b] && (top_tok == st.end_id || t == T - 1)) {
+      const int* res = st.seq[nxt] + (size_t)rows0 * (T + 1);
+      const int len = (top_tok == st.end_id) ? t : t + 1;             // strip <start> and a trailing <end>
+      for (int j = lane; j < len; j += 32) st.out_ids[(size_t)b * T + j] = res[1 + j];
+      __syncwarp();
+      if (lane == 0) {
+        st.out_len[b] = len;
+        st.done[b] = 1;
+        atomicAdd(st.n_done, 1);
+      }
     }
-  }
-  // last block to finish advances the step counter
-  if (lane == 0) {
-    __threadfence();
-    const int prev = atomicAdd(st.n_done + 1, 1);
-    if (prev == st.B - 1) {
-      st.n_done[1] = 0;
-      *st.step = t + 1;
+    // last block to finish advances the step counter
+    if (lane == 0) {
+      __threadfence();
+      const int prev = atomicAdd(st.n_done + 1, 1);
+      if (prev == st.B - 1) {
+        st.n_done[1] = 0;
+        *st.step = t + 1;
+      }
     }
   }
 }
 int launch_beam_merge(const BeamState& st, cudaStream_t s) {
-  k_beam_merge<<<st.B, 32, 0, s>>>(st);
-  LAUNCH_CHECK();
+  FPNMT_CUDA_OK(launch_k(k_beam_merge, dim3(st.B), dim3(MERGE_WARPS * 32), 0, s, st));
   return 0;
 }
 
 // dst[row][0..step][:] = src[src_row[row]][0..step][:]   (16-byte vectors; grid-stride)
 __global__ void k_kv_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ src_row,
                             int rows, int T, int row_vec, const int* __restrict__ step) {
+  pdl_launch();
+  pdl_wait();
   const int t = *step;   // positions 0..t are live
   const size_t per_row = (size_t)(t + 1) * row_vec;
   const size_t total = (size_t)rows * per_row;
@@ -298,9 +330,8 @@ __global__ void k_kv_gather(const uint4* __restrict__ src, uint4* __restrict__ d
 int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
                      cudaStream_t s) {
   const int row_vec = row_elems / 8;
-  k_kv_gather<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), src_row, rows,
-                                      T, row_vec, step);
-  LAUNCH_CHECK();
+  FPNMT_CUDA_OK(launch_k(k_kv_gather, dim3(148 * 8), dim3(256), 0, s, reinterpret_cast<const uint4*>(src),
+                         reinterpret_cast<uint4*>(dst), src_row, rows, T, row_vec, step));
   return 0;
 }
 

@@ -101,6 +101,32 @@ __device__ __forceinline__ void st_act8(const Act& a, size_t pix, int c, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel calls pdl_wait() before touching memory written by the
+// previous kernel in the stream and pdl_launch() as early as possible, so that the launch latency and the
+// prologue of kernel k+1 overlap the execution of kernel k.  Without the launch attribute both are no-ops.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // FPNMT_PDL=0 disables the launch attribute (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // warp helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -9,6 +9,8 @@ static inline int nblocks(size_t work, int threads) { return (int)((work + threa
 // ---------------------------------------------------------------------------------------- im2col (stem)
 __global__ void k_im2col_stem(const float* const* __restrict__ img_slot, int N, int H, int W, int kh, int kw, int stride, int pad_t,
                               int pad_l, int Ho, int Wo, Act out) {
+  pdl_launch();
+  pdl_wait();
   const float* __restrict__ img = *img_slot;
   const int groups = out.C / 8;
   const size_t total = (size_t)N * Ho * Wo * groups;
@@ -40,7 +42,7 @@ __global__ void k_im2col_stem(const float* const* __restrict__ img_slot, int N, 
 int launch_im2col_stem(const float* const* img, int N, int H, int W, int kh, int kw, int stride, int pad_t, int pad_l, int Ho,
                        int Wo, Act out, cudaStream_t s) {
   const size_t total = (size_t)N * Ho * Wo * (out.C / 8);
-  k_im2col_stem<<<nblocks(total, 256), 256, 0, s>>>(img, N, H, W, kh, kw, stride, pad_t, pad_l, Ho, Wo, out);
+  FPNMT_CUDA_OK(launch_k(k_im2col_stem, dim3(nblocks(total, 256)), dim3(256), 0, s, img, N, H, W, kh, kw, stride, pad_t, pad_l, Ho, Wo, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -48,6 +50,8 @@ int launch_im2col_stem(const float* const* img, int N, int H, int W, int kh, int
 // ---------------------------------------------------------------------------------------- pooling
 __global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
                           int zero_pad, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int groups = in.C / 8;
   const size_t total = (size_t)N * Ho * Wo * groups;
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -82,12 +86,14 @@ __global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pa
 int launch_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, bool zero_pad,
                    Act out, cudaStream_t s) {
   const size_t total = (size_t)N * Ho * Wo * (in.C / 8);
-  k_maxpool<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out);
+  FPNMT_CUDA_OK(launch_k(k_maxpool, dim3(nblocks(total, 256)), dim3(256), 0, s, in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void k_avgpool2(Act in, int N, int H, int W, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int groups = in.C / 8;
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)N * Ho * Wo * groups;
@@ -112,12 +118,14 @@ __global__ void k_avgpool2(Act in, int N, int H, int W, Act out) {
 }
 int launch_avgpool2(Act in, int N, int H, int W, Act out, cudaStream_t s) {
   const size_t total = (size_t)N * (H / 2) * (W / 2) * (in.C / 8);
-  k_avgpool2<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, out);
+  FPNMT_CUDA_OK(launch_k(k_avgpool2, dim3(nblocks(total, 256)), dim3(256), 0, s, in, N, H, W, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void k_subsample2(Act in, int N, int H, int W, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int groups = in.C / 8;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const size_t total = (size_t)N * Ho * Wo * groups;
@@ -136,7 +144,7 @@ __global__ void k_subsample2(Act in, int N, int H, int W, Act out) {
 }
 int launch_subsample2(Act in, int N, int H, int W, Act out, cudaStream_t s) {
   const size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (in.C / 8);
-  k_subsample2<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, out);
+  FPNMT_CUDA_OK(launch_k(k_subsample2, dim3(nblocks(total, 256)), dim3(256), 0, s, in, N, H, W, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -144,6 +152,8 @@ int launch_subsample2(Act in, int N, int H, int W, Act out, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------- depthwise 3x3
 __global__ void k_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int pad_l, int Ho, int Wo,
                                const float* __restrict__ w, const float* __restrict__ bias, int act, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int C = in.C;
   const int groups = C / 8;
   const size_t total = (size_t)N * Ho * Wo * groups;
@@ -180,7 +190,7 @@ __global__ void k_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_
 int launch_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int pad_l, int Ho, int Wo, const float* w,
                         const float* bias, int act, Act out, cudaStream_t s) {
   const size_t total = (size_t)N * Ho * Wo * (in.C / 8);
-  k_depthwise3x3<<<nblocks(total, 256), 256, 0, s>>>(in, N, H, W, stride, pad_t, pad_l, Ho, Wo, w, bias, act, out);
+  FPNMT_CUDA_OK(launch_k(k_depthwise3x3, dim3(nblocks(total, 256)), dim3(256), 0, s, in, N, H, W, stride, pad_t, pad_l, Ho, Wo, w, bias, act, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -188,6 +198,8 @@ int launch_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int 
 // ---------------------------------------------------------------------------------------- BN+ReLU (pre-activation)
 __global__ void k_scale_shift_relu(Act in, size_t pixels, const float* __restrict__ scale,
                                    const float* __restrict__ shift, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int groups = in.C / 8;
   const size_t total = pixels * groups;
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -202,7 +214,7 @@ __global__ void k_scale_shift_relu(Act in, size_t pixels, const float* __restric
 }
 int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const float* shift, Act out, cudaStream_t s) {
   const size_t total = pixels * (in.C / 8);
-  k_scale_shift_relu<<<nblocks(total, 256), 256, 0, s>>>(in, pixels, scale, shift, out);
+  FPNMT_CUDA_OK(launch_k(k_scale_shift_relu, dim3(nblocks(total, 256)), dim3(256), 0, s, in, pixels, scale, shift, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -211,6 +223,8 @@ int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const flo
 // grid (chunks, N); each block recomputes the image's softmax statistics (HW <= 4096 scores, L2 resident)
 // and scales `pix_per_block` pixels x C channels.
 __global__ void k_coattention(Act score, Act cls, int HW, int pix_per_block, Act out) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[32];
   __shared__ float s_max, s_inv;
   const int n = blockIdx.y;
@@ -259,7 +273,7 @@ __global__ void k_coattention(Act score, Act cls, int HW, int pix_per_block, Act
 int launch_coattention(Act score, Act cls, int N, int HW, Act out, cudaStream_t s) {
   const int ppb = 32;
   dim3 grid((HW + ppb - 1) / ppb, N);
-  k_coattention<<<grid, 256, 0, s>>>(score, cls, HW, ppb, out);
+  FPNMT_CUDA_OK(launch_k(k_coattention, dim3(grid), dim3(256), 0, s, score, cls, HW, ppb, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -299,6 +313,8 @@ __device__ __forceinline__ void ln_row_512(LoadFn load, const float* __restrict_
 
 __global__ void k_tokens_ln_pos(Act in, int HW, size_t rows, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, const float* __restrict__ pos, Act out) {
+  pdl_launch();
+  pdl_wait();
   const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -312,13 +328,15 @@ int launch_tokens_ln_pos(Act in, int N, int HW, const float* gamma, const float*
     return 1;
   }
   const size_t rows = (size_t)N * HW;
-  k_tokens_ln_pos<<<nblocks(rows, 8), 256, 0, s>>>(in, HW, rows, gamma, beta, eps, pos, out);
+  FPNMT_CUDA_OK(launch_k(k_tokens_ln_pos, dim3(nblocks(rows, 8)), dim3(256), 0, s, in, HW, rows, gamma, beta, eps, pos, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void k_layernorm_rows(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -337,7 +355,7 @@ int launch_layernorm_rows(const float* x, int rows, int C, const float* gamma, c
     set_last_error("layernorm_rows: d_model must be 512");
     return 1;
   }
-  k_layernorm_rows<<<nblocks(rows, 8), 256, 0, s>>>(x, rows, gamma, beta, eps, out);
+  FPNMT_CUDA_OK(launch_k(k_layernorm_rows, dim3(nblocks(rows, 8)), dim3(256), 0, s, x, rows, gamma, beta, eps, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -345,6 +363,8 @@ int launch_layernorm_rows(const float* x, int rows, int C, const float* gamma, c
 // ---------------------------------------------------------------------------------------- embedding + position
 __global__ void k_embed_pos(const int* __restrict__ tokens, const float* __restrict__ emb, const float* __restrict__ pos,
                             const int* __restrict__ step, int rows, int C, Act out) {
+  pdl_launch();
+  pdl_wait();
   const int groups = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * groups) return;
@@ -359,29 +379,33 @@ __global__ void k_embed_pos(const int* __restrict__ tokens, const float* __restr
 }
 int launch_embed_pos(const int* tokens, const float* emb, const float* pos, const int* step, int rows, int C, Act out,
                      cudaStream_t s) {
-  k_embed_pos<<<nblocks((size_t)rows * (C / 8), 256), 256, 0, s>>>(tokens, emb, pos, step, rows, C, out);
+  FPNMT_CUDA_OK(launch_k(k_embed_pos, dim3(nblocks((size_t)rows * (C / 8), 256)), dim3(256), 0, s, tokens, emb, pos, step, rows, C, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------- conversions
 __global__ void k_f32_to_act(const float* __restrict__ x, size_t rows, int C, Act out) {
+  pdl_launch();
+  pdl_wait();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= rows * C) return;
   st_act(out, idx / C, (int)(idx % C), x[idx]);
 }
 int launch_f32_to_act(const float* x, size_t rows, int C, Act out, cudaStream_t s) {
-  k_f32_to_act<<<nblocks(rows * C, 256), 256, 0, s>>>(x, rows, C, out);
+  FPNMT_CUDA_OK(launch_k(k_f32_to_act, dim3(nblocks(rows * C, 256)), dim3(256), 0, s, x, rows, C, out));
   LAUNCH_CHECK();
   return 0;
 }
 __global__ void k_act_to_f32(Act in, size_t rows, float* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= rows * in.C) return;
   out[idx] = ld_act(in, idx / in.C, (int)(idx % in.C));
 }
 int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s) {
-  k_act_to_f32<<<nblocks(rows * in.C, 256), 256, 0, s>>>(in, rows, out);
+  FPNMT_CUDA_OK(launch_k(k_act_to_f32, dim3(nblocks(rows * in.C, 256)), dim3(256), 0, s, in, rows, out));
   LAUNCH_CHECK();
   return 0;
 }

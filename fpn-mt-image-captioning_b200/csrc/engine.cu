@@ -12,6 +12,7 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -157,7 +158,7 @@ int Engine::upload_gemm(const std::vector<float>& wt, const std::vector<float>& 
   if (!out->w) return FPNMT_ERR_CUDA;
   FPNMT_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   std::vector<float> b = bias;
-  b.resize((size_t)(Cout + 7) / 8 * 8, 0.f);
+  b.resize((size_t)(Cout + 31) / 32 * 32, 0.f);   // the epilogue reads bias in 32-column units
   RC(upload_f32(b, &out->bias));
   out->Cout = Cout;
   out->K = K;
@@ -283,6 +284,13 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   if (res) r = res->a;
   // a K-padded weight (stem im2col) is addressed with Cin == K
   RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_));
+  if (const char* dn = getenv("FPNMT_DBG_OP")) {
+    if (name == dn) {
+      dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
+      cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+      op.p.dbg = dbg_buf_;
+    }
+  }
   Op o;
   o.name = name;
   o.kind = "igemm";
@@ -1045,31 +1053,45 @@ int Engine::generate(const float* images, int on_host, int32_t* out_ids, int32_t
 }
 
 // --------------------------------------------------------------------------------------------- profiling
+// Busy-wait kernel: keeps the GPU occupied while the host enqueues the whole timed program, so that the CUDA-event
+// intervals measure device execution only (no host launch gaps).
+__global__ void k_spin(long long ns) {
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
 int Engine::profile_program(Program& p, int iters, std::string& json, const char* label) {
-  cudaEvent_t e0, e1;
-  FPNMT_CUDA_OK(cudaEventCreate(&e0));
-  FPNMT_CUDA_OK(cudaEventCreate(&e1));
   cudaStream_t s = cap_stream_;
+  const size_t n = p.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) FPNMT_CUDA_OK(cudaEventCreate(&e));
+  std::vector<int> reps(n);
+  size_t total_launches = 0;
+  for (size_t i = 0; i < n; ++i) {
+    reps[i] = p[i].idempotent ? iters : 1;
+    total_launches += reps[i];
+  }
+  k_spin<<<1, 1, 0, s>>>((long long)(total_launches * 6000 + 200000));   // ~6 us of host time per launch
+  FPNMT_CUDA_OK(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    for (int r = 0; r < reps[i]; ++r) RC(p[i].run(s));
+    FPNMT_CUDA_OK(cudaEventRecord(ev[i + 1], s));
+  }
+  FPNMT_CUDA_OK(cudaStreamSynchronize(s));
   json += std::string("\"") + label + "\": [";
-  bool first = true;
-  for (auto& op : p) {
-    const int n = op.idempotent ? iters : 1;
-    if (op.idempotent) RC(op.run(s));   // warm
-    FPNMT_CUDA_OK(cudaEventRecord(e0, s));
-    for (int i = 0; i < n; ++i) RC(op.run(s));
-    FPNMT_CUDA_OK(cudaEventRecord(e1, s));
-    FPNMT_CUDA_OK(cudaEventSynchronize(e1));
+  for (size_t i = 0; i < n; ++i) {
     float ms = 0;
-    FPNMT_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    FPNMT_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     char buf[512];
     snprintf(buf, sizeof buf, "%s{\"name\": \"%s\", \"kind\": \"%s\", \"us\": %.3f, \"flops\": %.6g, \"bytes\": %.6g}",
-             first ? "" : ", ", op.name.c_str(), op.kind.c_str(), ms * 1000.0 / n, op.flops, op.bytes);
+             i ? ", " : "", p[i].name.c_str(), p[i].kind.c_str(), ms * 1000.0 / reps[i], p[i].flops, p[i].bytes);
     json += buf;
-    first = false;
   }
   json += "]";
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 
@@ -1093,6 +1115,17 @@ int Engine::profile(int iters, char* buf, size_t cap) {
   snprintf(tail, sizeof tail, ", \"decode_step_t\": %d, \"device_bytes\": %zu}", warm, alloc_bytes_);
   json += tail;
   FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+  if (dbg_buf_) {   // FPNMT_DBG_OP timeline of the last 8 instances (ns relative to each instance's entry)
+    long long h[16 * 9];
+    cudaMemcpy(h, dbg_buf_, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[fpnmt dbg] %lld instances; stamps: entry setup pdl_wait first_full mma_issued tfull res_ready epi_done end\n", h[0]);
+    for (int i = 0; i < 8; ++i) {
+      const long long* t = h + 16 + i * 16;
+      fprintf(stderr, "[fpnmt dbg] inst slot %d entry@%lld:", i, t[0]);
+      for (int k = 1; k <= 8; ++k) fprintf(stderr, " %6lld", t[k] ? t[k] - t[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   if (cap == 0) return fail(FPNMT_ERR_INVALID, "profile: zero capacity");
   const size_t n = std::min(cap - 1, json.size());
   memcpy(buf, json.data(), n);

@@ -88,6 +88,7 @@ class Engine {
   float* forced_logits_ = nullptr;        // [B][T][V]
   int* h_pinned_ = nullptr;               // pinned scratch for n_done polling
   float* step_scores_ = nullptr;
+  long long* dbg_buf_ = nullptr;          // FPNMT_DBG_OP timeline buffer
 
   // helpers
   void* dalloc(size_t bytes);

@@ -1,20 +1,54 @@
-// tcgen05 implicit-GEMM kernel (see igemm.cuh).  Warp-specialised, persistent:
-//   warp 0      : TMA producer  (one elected lane)  global -> smem ring (A box + B box per stage)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane), tcgen05.mma 128 x BN x 16, fp32 in TMEM
-//   warps 2..5  : epilogue, TMEM -> registers (tcgen05.ld 32x32b.x32) -> bias/residual/activation -> global
+// tcgen05 implicit-GEMM kernel (see igemm.cuh).  Warp-specialised, persistent, 320 threads:
+//   warp 0      : TMA producer (one lane): global -> smem ring (A box + B box per stage).  The weight (B) boxes of the
+//                 first ring pass are issued BEFORE griddepcontrol.wait (weights are static), so under programmatic
+//                 dependent launch they stream in while the previous kernel is still running.
+//   warp 1      : TMEM allocator + MMA issuer (one lane): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM.
+//   warps 2..9  : epilogue.  Warp e owns TMEM lane quarter (warp_id % 4) and one half of the tile's columns.
+//                 Per 32-column unit: tcgen05.ld -> registers; + bias; + residual (prefetched with cp.async into a
+//                 swizzled per-warp staging buffer while the MMAs of the tile are still running); activation; bf16
+//                 pack -> staging buffer -> TRANSPOSED 16-byte global stores (8 rows x 64 contiguous bytes per warp
+//                 instruction: full 32 B sectors, instead of 32 rows x 16 B).
 // Two TMEM accumulator buffers (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "igemm.cuh"
 
 namespace fpnmt {
 
 constexpr int A_STAGE_BYTES = IG_BM * IG_BK * 2;   // 16 KB
+constexpr int EPI_WARPS = 8;
+constexpr int UNIT_BYTES = 32 * 64;                // 32 rows x 32 bf16 columns
 
-__host__ __device__ constexpr int ig_stages(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+__host__ __device__ constexpr int ig_stages(int BN) { return BN == 256 ? 3 : (BN == 128 ? 5 : (BN == 64 ? 6 : 8)); }
 __host__ __device__ constexpr int ig_b_bytes(int BN) { return BN * IG_BK * 2; }
+__host__ __device__ constexpr int ig_units_per_warp(int BN) { return BN >= 64 ? BN / 64 : 1; }
 
 int igemm_stages(int BN) { return ig_stages(BN); }
 size_t igemm_smem_bytes(int BN) {
-  return (size_t)ig_stages(BN) * (A_STAGE_BYTES + ig_b_bytes(BN)) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return (size_t)ig_stages(BN) * (A_STAGE_BYTES + ig_b_bytes(BN)) + (size_t)EPI_WARPS * ig_units_per_warp(BN) * UNIT_BYTES +
+         (size_t)EPI_WARPS * 32 * 2 * sizeof(long long) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+// staging buffer addressing: row r (0..31) holds 4 chunks of 16 B; chunk c is stored at slot c ^ ((r >> 1) & 3) so that
+// both "thread = row" and "8 rows x 4 chunks" access patterns are bank-conflict free.
+__device__ __forceinline__ uint4* stage_ptr(uint8_t* buf, int r, int c) {
+  return reinterpret_cast<uint4*>(buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
 template <int BN>
@@ -24,13 +58,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   constexpr int STAGES = ig_stages(BN);
   constexpr int B_STAGE_BYTES = ig_b_bytes(BN);
   constexpr int TMEM_COLS = 2 * BN;
+  constexpr int UPW = ig_units_per_warp(BN);       // 32-column units per epilogue warp
+  constexpr int UNITS = BN / 32;
   constexpr uint32_t IDESC = umma_idesc_bf16(IG_BM, BN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);                 // [EPI_WARPS][UPW][UNIT_BYTES]
+  long long* sOff = reinterpret_cast<long long*>(sStage + EPI_WARPS * UPW * UNIT_BYTES);   // [EPI_WARPS][2][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOff + EPI_WARPS * 64);
   uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
@@ -40,6 +78,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  __shared__ long long* s_dbg;
+  if (threadIdx.x == 0) {
+    s_dbg = nullptr;
+    if (p.dbg && blockIdx.x == 0) {
+      const long long inst = (long long)atomicAdd((unsigned long long*)p.dbg, 1ull);
+      s_dbg = p.dbg + 16 + (inst % 8) * 16;
+      s_dbg[0] = gtimer();
+    }
+  }
+#define DBG(k) do { if (s_dbg) s_dbg[k] = gtimer(); } while (0)
+
+  pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB);
@@ -50,7 +100,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -59,6 +109,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG(1);
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = tiles_m * p.tiles_co;
@@ -67,9 +118,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    if (lane == 0 && (int)blockIdx.x < total_tiles) {
+      // weights of the first ring pass of the first tile: static data, fetched before the grid dependency resolves
+      const int npre = kiters < STAGES ? kiters : STAGES;
+      {
+        const int co_t = blockIdx.x % p.tiles_co;
+        for (int it = 0; it < npre; ++it) {
+          const int kc = it % p.kchunks;
+          const int t = (it / p.kchunks) % taps;
+          const int term = it / (p.kchunks * taps);
+          const int bko = (term == 1) ? p.b_lo_off : 0;
+          mbar_expect_tx(&full_bar[it], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sB + it * B_STAGE_BYTES, &tmB, &full_bar[it], bko + t * p.Cin + kc * IG_BK, co_t * BN);
+        }
+      }
+      pdl_wait();
+      DBG(2);
+      int git = 0;   // k-iterations issued so far by this CTA
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int co_t = tile % p.tiles_co;
         int mt = tile / p.tiles_co;
@@ -84,16 +149,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int t = 0; t < taps; ++t) {
             const int dy = t / p.taps_x - p.pad_y;
             const int dx = t % p.taps_x - p.pad_x;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-              tma_load_4d(sA + stage * A_STAGE_BYTES, ma, &full_bar[stage], kc * IG_BK, x0 + dx, y0 + dy, n0);
-              tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK,
-                          co_t * BN);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
+            for (int kc = 0; kc < p.kchunks; ++kc, ++git) {
+              const int stage = git % STAGES;
+              if (git >= npre) {
+                mbar_wait(&empty_bar[stage], ((git / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK, co_t * BN);
               }
+              tma_load_4d(sA + stage * A_STAGE_BYTES, ma, &full_bar[stage], kc * IG_BK, x0 + dx, y0 + dy, n0);
             }
           }
         }
@@ -113,6 +176,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0) DBG(3);
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
@@ -126,6 +190,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             phase ^= 1;
           }
         }
+        DBG(4);
         umma_commit(&tfull_bar[acc]);       // accumulator ready for the epilogue
         if (++acc == 2) {
           acc = 0;
@@ -134,14 +199,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, 128 rows)
+    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
+    const int e = warp - 2;
     const int quarter = warp & 3;           // TMEM lane window this warp may access
+    const int half = e >> 2;                // which half of the tile's columns
     const int row = quarter * 32 + lane;
     const int r_tx = row % p.tw;
     const int r_ty = (row / p.tw) % p.th;
     const int r_bn = row / (p.tw * p.th);
+    uint8_t* my_stage = sStage + e * UPW * UNIT_BYTES;
+    long long* my_off = sOff + e * 64;      // [0..31] output pixel, [32..63] residual pixel (-1 = invalid row)
+    const int u0 = (UNITS >= 2) ? half * (UNITS / 2) : 0;
+    const int nu = (UNITS >= 2) ? UNITS / 2 : (half == 0 ? 1 : 0);
+    const bool fast = (p.Cout & 7) == 0;    // 16-byte vector path needs Cout % 8 == 0
+    const int t_r = lane >> 2, t_c = lane & 3;   // transposed mapping: 8 rows x 4 chunks per warp instruction
     int acc = 0;
     uint32_t acc_phase = 0;
+    pdl_wait();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int co_t = tile % p.tiles_co;
       int mt = tile / p.tiles_co;
@@ -154,60 +228,164 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const size_t pix = ((size_t)n * p.H + y) * p.W + x;
       size_t rpix = pix;
       if (p.res_mode == RES_UP2) rpix = ((size_t)n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-
+      __syncwarp();
+      my_off[lane] = valid ? (long long)pix : -1;
+      my_off[32 + lane] = valid ? (long long)rpix : -1;
+      __syncwarp();
+      // residual prefetch for every unit of this warp (in flight while the tile's MMAs are still running)
+      if (p.res_mode != RES_NONE && fast) {
+        for (int j = 0; j < nu; ++j) {
+          const int col0 = co_t * BN + (u0 + j) * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + t_r;
+            const long long off = my_off[32 + rr];
+            const int col = col0 + t_c * 8;
+            const bool ok = off >= 0 && col < p.Cout;
+            const bf16* src = p.res.p + (ok ? (size_t)off * p.res.ld + col : 0);
+            cp_async16(stage_ptr(my_stage + j * UNIT_BYTES, rr, t_c), src, ok);
+          }
+          cp_async_commit();
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (e == 0 && lane == 0) DBG(5);
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int j = 0; j < nu; ++j) {
         uint32_t r[32];
-        tmem_ld32(t_addr + ch * 32, r);
+        tmem_ld32(t_addr + (u0 + j) * 32, r);
         tmem_ld_wait();
-        const int col0 = co_t * BN + ch * 32;
-        if (valid && col0 < p.Cout) {
+        const int col0 = co_t * BN + (u0 + j) * 32;
+        if (col0 >= p.Cout) continue;        // warp-uniform
+        uint8_t* buf = my_stage + j * UNIT_BYTES;
+        float v[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = col0 + g * 8;
-            if (c >= p.Cout) break;
-            float v[8];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (fast) {
+          // ---- bias (bias arrays are padded to a multiple of 32 floats)
+          if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-            if (c + 8 <= p.Cout) {
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.res_mode != RES_NONE) {
-                float rr[8];
-                ld_act8(p.res, rpix, c, rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += rr[i];
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
-              if (p.out.p) st_act8(p.out, pix, c, v);
-              if (p.out_f32) {
-                float* o = p.out_f32 + pix * (size_t)p.ld_f32 + c;
-                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              }
-            } else {
-              for (int i = 0; i < 8 && c + i < p.Cout; ++i) {   // ragged tail of the channel range
-                float t = v[i];
-                if (p.bias) t += p.bias[c + i];
-                if (p.res_mode != RES_NONE) t += ld_act(p.res, rpix, c + i);
-                t = apply_act(t, p.act);
-                if (p.out.p) st_act(p.out, pix, c + i, t);
-                if (p.out_f32) p.out_f32[pix * (size_t)p.ld_f32 + c + i] = t;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + i * 4);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
+          }
+          // ---- residual
+          if (p.res_mode != RES_NONE) {
+            cp_async_wait_pending(nu - 1 - j);
+            __syncwarp();
+            if (e == 0 && lane == 0) DBG(6);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float f[8];
+              unpack8(*stage_ptr(buf, lane, c), f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
+            }
+            __syncwarp();
+            if (p.res.lo) {                  // split residual: low halves, synchronous transposed load
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + t_r;
+                const long long off = my_off[32 + rr];
+                const int col = col0 + t_c * 8;
+                const bool ok = off >= 0 && col < p.Cout;
+                const bf16* src = p.res.p + p.res.lo + (ok ? (size_t)off * p.res.ld + col : 0);
+                cp_async16(stage_ptr(buf, rr, t_c), src, ok);
+              }
+              cp_async_commit();
+              cp_async_wait_pending(0);
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float f[8];
+                unpack8(*stage_ptr(buf, lane, c), f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
+              }
+              __syncwarp();
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          // ---- bf16 output through the staging buffer, transposed 16-byte stores
+          if (p.out.p) {
+            uint4 hi[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              hi[c] = pack8(v + c * 8);
+              *stage_ptr(buf, lane, c) = hi[c];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + t_r;
+              const long long off = my_off[rr];
+              const int col = col0 + t_c * 8;
+              if (off >= 0 && col < p.Cout)
+                *reinterpret_cast<uint4*>(p.out.p + (size_t)off * p.out.ld + col) = *stage_ptr(buf, rr, t_c);
+            }
+            __syncwarp();
+            if (p.out.lo) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float hf[8], lo[8];
+                unpack8(hi[c], hf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) lo[i] = v[c * 8 + i] - hf[i];
+                *stage_ptr(buf, lane, c) = pack8(lo);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + t_r;
+                const long long off = my_off[rr];
+                const int col = col0 + t_c * 8;
+                if (off >= 0 && col < p.Cout)
+                  *reinterpret_cast<uint4*>(p.out.p + p.out.lo + (size_t)off * p.out.ld + col) = *stage_ptr(buf, rr, t_c);
+              }
+              __syncwarp();
+            }
+          }
+          // ---- fp32 output: two 16-column halves (64 B per row each) through the same buffer
+          if (p.out_f32) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *stage_ptr(buf, lane, c) = make_uint4(__float_as_uint(v[hh * 16 + c * 4]), __float_as_uint(v[hh * 16 + c * 4 + 1]),
+                                                      __float_as_uint(v[hh * 16 + c * 4 + 2]), __float_as_uint(v[hh * 16 + c * 4 + 3]));
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + t_r;
+                const long long off = my_off[rr];
+                const int col = col0 + hh * 16 + t_c * 4;
+                if (off >= 0 && col < p.Cout)
+                  *reinterpret_cast<uint4*>(p.out_f32 + (size_t)off * p.ld_f32 + col) = *stage_ptr(buf, rr, t_c);
+              }
+              __syncwarp();
+            }
+          }
+        } else if (valid) {
+          // ---- generic scalar path (Cout not a multiple of 8, e.g. the 1-channel score map)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (col0 + i >= p.Cout) break;
+            float t = v[i];
+            if (p.bias) t += p.bias[col0 + i];
+            if (p.res_mode != RES_NONE) t += ld_act(p.res, rpix, col0 + i);
+            t = apply_act(t, p.act);
+            if (p.out.p) st_act(p.out, pix, col0 + i, t);
+            if (p.out_f32) p.out_f32[pix * (size_t)p.ld_f32 + col0 + i] = t;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (e == 0 && lane == 0) DBG(7);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -217,16 +395,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG(8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+#undef DBG
 }
 
 template <int BN>
 static int launch_bn(const IgemmOp& op, cudaStream_t stream) {
-  igemm_kernel<BN><<<op.grid, IG_THREADS, igemm_smem_bytes(BN), stream>>>(op.tmA_hi, op.tmA_lo, op.tmB, op.p);
-  FPNMT_CUDA_OK(cudaGetLastError());
+  FPNMT_CUDA_OK(launch_k(igemm_kernel<BN>, dim3(op.grid), dim3(IG_THREADS), igemm_smem_bytes(BN), stream, op.tmA_hi,
+                         op.tmA_lo, op.tmB, op.p));
   return 0;
 }
 

@@ -11,7 +11,7 @@ namespace fpnmt {
 
 constexpr int IG_BM = 128;   // rows (pixels) per CTA tile == UMMA_M == TMEM lanes
 constexpr int IG_BK = 64;    // K elements per pipeline stage == one 128 B swizzle row of bf16
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 
 enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };
 
@@ -33,6 +33,7 @@ struct IgemmParams {
   int ld_f32;
   int res_mode;                   // ResMode; residual is added before the activation
   Act res;                        // RES_SAME: same pixel grid; RES_UP2: (N, H/2, W/2) nearest-upsampled
+  long long* dbg;                 // optional timeline buffer (globaltimer stamps of block 0), normally nullptr
 };
 
 struct IgemmOp {

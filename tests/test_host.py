@@ -184,10 +184,14 @@ print("rank", rank, "ok", lo, hi)
 
 
 def test_allgather_world_size_2_gloo(tmp_path):
+    import socket
     script = tmp_path / "w.py"
     script.write_text(_GLOO_WORKER % {"root": ROOT})
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok 0 5" in r.stdout and "rank 1 ok 5 10" in r.stdout
