@@ -23,3 +23,4 @@ from .ops import *            # noqa: F401,F403
 from .backbones import *      # noqa: F401,F403
 from .model import *          # noqa: F401,F403
 from .decode import *         # noqa: F401,F403
+from .testing import *        # noqa: F401,F403

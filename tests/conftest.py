@@ -37,15 +37,8 @@ def built_lib():
     return mod.build(force=False, verbose=False)
 
 
-TEST_GAINS = {"/model/conv2d_4": 48.0, "/model/conv2d_5": 48.0, "pyramid_regression": 20.0, "pyramid_classification": 20.0,
-              "final_layer": 6.0}
-
-
 def small_weights(backbone, vocab=512, layers=2, seed=0):
-    """Random weights with non-trivial BN statistics / biases and gains that keep every stage's signal O(1)
-    (at Keras-default init the co-attention's 1/(H*W) scale makes head outputs vanish)."""
-    from fpnmt.weights import init_weights
-    gains = dict(TEST_GAINS)
-    if backbone == "resnet50":
-        gains.update({"_branch2c": 0.25, "C5_reduced": 0.01, "C4_reduced": 0.02, "C3_reduced": 0.1})
-    return init_weights(backbone, vocab=vocab, seed=seed, num_layers=layers, randomize_bn=True, bias_std=0.02, gains=gains)
+    """Test weights: reference variable tree and distributions, gains + calibrated BatchNorm statistics so that every
+    stage carries an O(1) input-dependent signal (see oracle/fpnmt_oracle/testing.py)."""
+    import fpnmt_oracle as O
+    return O.test_weights(backbone, vocab=vocab, layers=layers, seed=seed)

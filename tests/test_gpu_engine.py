@@ -32,7 +32,7 @@ def setup(request):
     bb = request.param
     w = small_weights(bb, V, L)
     Wv = O.W(w)
-    img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    img = O.test_images(B, S, seed=1)
     taps = {}
     mem_ref = O.encoder(img, Wv, bb, num_layers=L, input_vocab_size=(S // 16) ** 2, taps=taps)
     return dict(bb=bb, w=w, Wv=Wv, img=img, taps=taps, mem_ref=mem_ref)
@@ -95,7 +95,7 @@ def test_generate_matches_faithful_reference_loop_prob_scores():
     bb = "mobilenet224_1.0"
     w = small_weights(bb, V, L, seed=11)
     Wv = O.W(w)
-    img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    img = O.test_images(B, S, seed=5)
     eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16x3",
                  score_mode="prob", use_graphs=True)
     ids, lens = eng.generate(img.cuda(), early_stop=True)
@@ -112,7 +112,7 @@ def test_end_token_early_stop_and_strip():
     b = w["transformer/final_layer/bias"].copy()
     b[3] = 60.0
     w["transformer/final_layer/bias"] = b
-    img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(6)) * 2 - 1
+    img = O.test_images(B, S, seed=6)
     eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16x3")
     ids, lens = eng.generate(img.cuda(), early_stop=True)
     ids2, lens2 = eng.generate(img.cuda(), early_stop=False)       # fixed-length run freezes finished images
@@ -128,8 +128,7 @@ def test_batch_invariance_and_determinism_512():
     from fpnmt.weights import init_weights
     bb, Bf, Nf, Vf, Tf = "mobilenet224_1.0", 4, 8, 1000, 12
     w = small_weights(bb, Vf, 2, seed=2)
-    g = torch.Generator().manual_seed(9)
-    imgs = torch.rand(Bf, 512, 512, 3, generator=g) * 2 - 1
+    imgs = O.test_images(Bf, 512, seed=9)
     eng = Engine(w, backbone=bb, batch=Bf, beam=Nf, vocab=Vf, max_len=Tf, num_layers=2, image_size=512, use_graphs=True)
     eng2 = Engine(w, backbone=bb, batch=Bf, beam=Nf, vocab=Vf, max_len=Tf, num_layers=2, image_size=512, use_graphs=False)
     m1 = eng.encode(imgs.cuda()).cpu()
@@ -160,7 +159,7 @@ def test_pipeline_mirror_end_to_end(tmp_path):
     save_weights(str(tmp_path / "weights.npz"), w)
     pipe = Pipeline(tok_path, str(tmp_path), 10, beam=4)
     assert pipe.target_vocab_size == vocab and pipe.max_seq_len == 10
-    img = (torch.rand(512, 512, 3, generator=torch.Generator().manual_seed(8)) * 2 - 1).numpy()
+    img = O.test_images(1, 512, seed=8)[0].numpy()
     ids, attn = pipe.predict(img, 10)
     assert attn is None and ids.ndim == 1 and len(ids) <= 10
     res = pipe.evaluate_img(img, 10)
@@ -172,3 +171,29 @@ def test_pipeline_mirror_end_to_end(tmp_path):
     mem = pipe.transformer.encoder(torch.from_numpy(img)[None], False, None)
     logits, _ = pipe.transformer(mem, torch.tensor([[2, 5, 9]]), False, None)
     assert tuple(logits.shape) == (1, 3, vocab + (-vocab) % 8)
+
+
+def test_engine_matches_reference_goldens():
+    """CUDA engine vs the golden vectors recorded from the reference's OWN modules (tests/golden/make_golden.py):
+    FeatureExtractor.call outputs, Encoder.call memory and Pipeline.predict token ids (beam 4 and 8)."""
+    import os
+    from fpnmt.engine import Engine
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model.npz")) as z:
+        gold = {k: z[k] for k in z.files}
+    Lg, Vg, Tg, Sg = (int(v) for v in gold["fe_cfg"])
+    w = O.test_weights("mobilenet224_1.0", vocab=Vg, layers=Lg, seed=0)
+    img = O.test_images(2, Sg, seed=int(gold["fe_image_seed"][0]))
+    for beam in (4, 8):
+        eng = Engine(w, backbone="mobilenet224_1.0", batch=2, beam=beam, vocab=Vg, max_len=Tg, num_layers=Lg, image_size=Sg,
+                     precision="bf16x3", score_mode="prob", use_graphs=True)
+        if beam == 4:
+            feats = eng.features(img.cuda())
+            for i in range(5):
+                assert rel(feats[i][:1].cpu(), torch.from_numpy(gold["fe_feat%d" % i])) < 3e-3, i
+            mem = eng.encode(img.cuda()).cpu()
+            assert rel(mem, torch.from_numpy(gold["fe_memory"])) < 3e-3
+            assert float((mem - torch.from_numpy(gold["fe_memory"])).abs().max()) < 2e-2
+        ids, lens = eng.generate(img.cuda(), early_stop=True)
+        for i in range(2):
+            assert ids[i, :lens[i]].tolist() == gold["predict_beam%d_img%d" % (beam, i)].tolist(), (beam, i)
+        eng.close()
