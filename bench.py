@@ -55,56 +55,87 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / power / throttle reasons sampled every 50 ms on a thread while the timed region runs (NVML in
+    process; `nvidia-smi` polling as the fallback)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.samples, self.started, self.how = gpu_index, [], False, None
+        self.stop_flag = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
-        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
         self.t = threading.Thread(target=self._poll, daemon=True)
         self.t.start()
-        self.proc = True
+        self.started = True
 
     def _poll(self):
-        cmd = ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"]
+        if self.nv is not None:
+            nv = self.nv
+            while not self.stop_flag.is_set():
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append((sm, self.sm_max, pw, rs))
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.05)
+            return
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        cmd = ["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + q, "--format=csv,noheader,nounits"]
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop_flag.is_set():
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=5)
-                self.lines.extend(l.strip() for l in r.stdout.splitlines() if l.strip())
+                for ln in r.stdout.splitlines():
+                    f = [x.strip() for x in ln.split(",")]
+                    if len(f) >= 7:
+                        rs = sum(b for b, v in zip(bits, f[3:7]) if v.lower().startswith("active"))
+                        self.samples.append((float(f[0]), float(f[1]), float(f[2]), rs))
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if not self.started:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"], "samples": 0}
         self.stop_flag.set()
         self.t.join(timeout=6)
-        sm, smax, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        sm = sorted(x[0] for x in self.samples)
+        reasons = set()
+        for x in self.samples:
+            for bit, name in self.REASONS.items():
+                if x[3] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((x[1] for x in self.samples), default=None),
+                "power_w_max": max((x[2] for x in self.samples), default=None), "samples": len(sm), "reasons": sorted(reasons),
+                "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_sample(wl: dict, steps: int, warmup: int, t_sample: int = 16):
+def cpu_reference_sample(wl: dict, steps: int, warmup: int, t_sample: int = 64):
     """The reference's own algorithm (oracle restatement: one image at a time, encoder once, decoder recomputed over
     the whole prefix each step, probability-product beam scores) on the host cores.  Bounded sample: each step
     captions ONE image with beam `wl['beam']` for `t_sample` decode steps (the full workload decodes 64)."""
@@ -129,8 +160,10 @@ def cpu_reference_sample(wl: dict, steps: int, warmup: int, t_sample: int = 16):
             times.append(dt)
     sec = sum(times) / len(times)
     return dict(value=1.0 / sec, unit="images/s", cores=cores, kind="port",
-                sample="1 image/step, beam=%d, %d of 64 decode steps (uncached, as utils/pipeline.py:105-112), "
-                       "%d timed steps, PyTorch CPU fp32, %d threads" % (wl["beam"], t_sample, len(times), cores),
+                sample="1 image of the %d-image batch per step (%s, 512x512), beam=%d, %d of %d decode steps, whole prefix "
+                       "recomputed each step (uncached, as utils/pipeline.py:105-112), %d timed steps after %d warm-up, "
+                       "PyTorch CPU fp32, %d threads" % (wl["batch"], wl["backbone"], wl["beam"], t_sample, wl["max_len"],
+                                                         len(times), warmup, cores),
                 sec_per_image=sec)
 
 
@@ -138,8 +171,8 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    steps = max(1, args.steps)
+    warm = max(1, args.warmup)
     cb = cpu_reference_sample(wl, steps, warm)
     line = {"metric": "captioned images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": cb["sec_per_image"] * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -246,7 +279,7 @@ def run_own(args, wl):
                 "encode_us_sum": enc_us, "decode_step_us_sum": step_us}
     cb = None
     if world == 1 and not args.no_cpu:
-        cb = cpu_reference_sample(wl, 1, 0)
+        cb = cpu_reference_sample(wl, 3, 1)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     flop_total = B * world * args.steps * (F_ENC[wl["backbone"]] + F_DEC)
     line = {"metric": "captioned images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "tgemm.cuh"
 
 namespace fpnmt {
 static thread_local std::string g_last_error;
@@ -28,7 +29,7 @@ struct fpnmt_handle {
 extern "C" {
 
 FPNMT_API const char* fpnmt_version(void) {
-  return "fpnmt 0.1 (sm_100a; tcgen05 implicit-GEMM igemm_kernel<32|64|128|256>, TMA, TMEM; CUDA-core tail kernels)";
+  return "fpnmt 0.1 (sm_100a; tcgen05 implicit-GEMM igemm_kernel<32|64|128|256> + skinny-row tgemm_kernel<32|64> (cluster LayerNorm epilogue), TMA, TMEM; CUDA-core tail kernels)";
 }
 FPNMT_API const char* fpnmt_last_error(void) { return g_last_error.c_str(); }
 
@@ -210,6 +211,81 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
   cleanup();
   if (!rc && e != cudaSuccess) {
     set_last_error(std::string("op_conv2d: ") + cudaGetErrorString(e));
+    return FPNMT_ERR_CUDA;
+  }
+  return rc;
+}
+
+// ---- stand-alone skinny-row Dense operator (tgemm) -----------------------------------------------------
+FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, int K, const float* kernel, int F,
+                   const float* bias, int act, const float* residual, const float* gamma, const float* beta, float eps,
+                   float* out, int force_bn, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K % 8 || F % 8) {
+    set_last_error("op_dense: K and F must be multiples of 8");
+    return FPNMT_ERR_INVALID;
+  }
+  FPNMT_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FPNMT_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("op_dense: device is not sm_100");
+    return FPNMT_ERR_CUDA;
+  }
+  int rc = tgemm_set_attributes();
+  if (rc) return rc;
+  const bool split = precision == FPNMT_PREC_BF16X3;
+  const size_t ldw = split ? 2 * (size_t)K : (size_t)K;
+  std::vector<uint16_t> hw((size_t)F * ldw);
+  for (int k = 0; k < K; ++k)
+    for (int o = 0; o < F; ++o) {
+      const float f = kernel[(size_t)k * F + o];          // Keras Dense kernel (in, out)
+      const uint16_t hi = f2bf_host(f);
+      hw[(size_t)o * ldw + k] = hi;
+      if (split) hw[(size_t)o * ldw + K + k] = f2bf_host(f - bf2f_host(hi));
+    }
+  std::vector<void*> tmp;
+  auto dal = [&](size_t b) {
+    void* p = nullptr;
+    cudaMalloc(&p, b ? b : 16);
+    tmp.push_back(p);
+    return p;
+  };
+  bf16* dw = (bf16*)dal(hw.size() * 2);
+  cudaMemcpyAsync(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice, s);
+  auto upl = [&](const float* h, int n) {
+    float* d = (float*)dal((size_t)(n + 128) * 4);
+    cudaMemsetAsync(d, 0, (size_t)(n + 128) * 4, s);
+    cudaMemcpyAsync(d, h, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    return d;
+  };
+  float* dbias = bias ? upl(bias, F) : nullptr;
+  float* dg = gamma ? upl(gamma, F) : nullptr;
+  float* db = beta ? upl(beta, F) : nullptr;
+  auto mk = [&](size_t rows, int C) {
+    Act a;
+    a.C = C;
+    a.ld = split ? 2 * C : C;
+    a.lo = split ? C : 0;
+    a.p = (bf16*)dal(rows * a.ld * 2);
+    return a;
+  };
+  Act ax = mk(R, K), ao = mk(R, F), ar{nullptr, 0, 0, 0};
+  rc = launch_f32_to_act(x, R, K, ax, s);
+  if (!rc && residual) {
+    ar = mk(R, F);
+    rc = launch_f32_to_act(residual, R, F, ar, s);
+  }
+  TgemmOp op;
+  if (!rc)
+    rc = make_tgemm_op(&op, R, ax, dw, F, K, split, dbias, act, ao, nullptr, 0, residual ? &ar : nullptr, dg, db, eps,
+                       prop.multiProcessorCount, force_bn);
+  if (!rc) rc = tgemm_launch(op, s);
+  if (!rc) rc = launch_act_to_f32(ao, R, out, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  for (void* p : tmp) cudaFree(p);
+  if (!rc && e != cudaSuccess) {
+    set_last_error(std::string("op_dense: ") + cudaGetErrorString(e));
     return FPNMT_ERR_CUDA;
   }
   return rc;

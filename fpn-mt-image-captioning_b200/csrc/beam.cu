@@ -1,11 +1,10 @@
-// Decode tail of one beam-search step (reference: /root/reference/utils/pipeline.py:115-148).
-//   phase 1  k_beam_rowtopk : per (image, beam) row of fp32 logits: max, sum-exp, candidate score
-//                             (prob mode: softmax * beam_prob; log mode: log_softmax + beam_logprob),
-//                             row-local top-N with tf.math.top_k tie order (lower index first).
-//                             128-bit loads, values kept in registers, warp-shuffle + smem reductions.
-//   phase 2  k_beam_merge   : per image merge N x N candidates (ties -> lower flat index n*V+v), emit
-//                             parent/token/score, reorder token sequences and the KV-cache ancestry table by
-//                             parent, handle <end> on the top beam, advance the device step counter.
+// Decode tail of one beam-search step (reference: /root/reference/utils/pipeline.py:115-148), ONE kernel per step:
+//   k_beam_step   phase 1: per (image, beam) row of fp32 logits: max, sum-exp, candidate score (prob mode:
+//                 softmax * beam_prob; log mode: log_softmax + beam_logprob), row-local top-N with tf.math.top_k tie
+//                 order (lower index first); 128-bit streaming loads, values kept in registers, warp-shuffle rounds.
+//                 phase 2 (last block of each image): merge N x N candidates (ties -> lower flat index n*V+v), emit
+//                 parent/token/score, reorder token sequences and the KV-cache ancestry table by parent, handle <end>
+//                 on the top beam, write the next step's embedding+position rows, advance the device step counter.
 //   k_kv_gather             : physical KV-cache reorder by parent (the bandwidth-bound alternative to the
 //                             ancestry table; used by the "physical" cache mode).
 #include "kernels.cuh"
@@ -29,6 +28,7 @@ __global__ void k_beam_init(BeamState st, int true_beam) {
   if (i < st.B) {
     st.done[i] = 0;
     st.out_len[i] = 0;
+    st.img_count[i] = 0;
   }
   if (i < rows) {
     const int n = i % st.N;
@@ -61,19 +61,27 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
-// Phase 1.  One block per (image, beam) row.  Row statistics with one block reduction each; then every WARP extracts
-// its own top-N with shuffle-only arg-max rounds (no block barrier), and warp 0 merges the NW*N survivors.
+// One launch per decode step.  grid = B*N blocks, one per (image, beam) row of logits:
+//   phase 1 (every block)  online softmax statistics of the row (one pass, one block reduction), candidate scores in
+//                          registers, per-WARP top-N by shuffle arg-max rounds in which only the owning lane rescans its
+//                          registers, then warp 0 merges the NW*N survivors -> cand_val/cand_idx[row][N] (sorted).
+//   phase 2 (last block of each image, elected by an atomic counter)  merge the N x N candidates (ties -> lower flat
+//                          index n*V+v), emit parent/token/score, reorder token sequences and the KV ancestry table,
+//                          handle <end>, write the NEXT step's decoder input rows (embedding + position), and let the
+//                          last image advance the device step counter.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const float* __restrict__ logits, int ld) {
+__global__ void __launch_bounds__(THREADS) k_beam_step(BeamState st, const float* __restrict__ logits, int ld, BeamEmbed em) {
   constexpr int NW = THREADS / 32;
-  __shared__ float s_red[NW];
+  __shared__ float s_m[NW], s_s[NW];
   __shared__ float s_cv[NW * 32];
   __shared__ int s_ci[NW * 32];
+  __shared__ int s_parent[32], s_token[32];
+  __shared__ int s_last;
   pdl_launch();
   pdl_wait();
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int V = st.V, N = st.N;
+  const int V = st.V, N = st.N, T = st.T;
   const int t = *st.step;
   const float score = st.score[t & 1][row];
   const float* x = logits + (size_t)row * ld;
@@ -83,57 +91,52 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
   for (int i = 0; i < RT_MAXV4; ++i) {
     const int e = (i * THREADS + tid) * 4;
     if (e + 3 < V) {
-      const float4 q = *reinterpret_cast<const float4*>(x + e);
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(x + e));
       v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[4 * i + j] = (e + j < V) ? x[e + j] : -INFINITY;
     }
   }
-  // row max
+  // ---- row max and sum of exponentials: thread-local (m, s) pairs combined with the online-softmax rule
   float m = -INFINITY;
 #pragma unroll
   for (int i = 0; i < RT_MAXV4 * 4; ++i) m = fmaxf(m, v[i]);
   m = warp_max(m);
-  if (lane == 0) s_red[warp] = m;
+  if (lane == 0) s_m[warp] = m;
   __syncthreads();
 #pragma unroll
-  for (int w = 0; w < NW; ++w) m = fmaxf(m, s_red[w]);
-  __syncthreads();
-  // sum exp
+  for (int w = 0; w < NW; ++w) m = fmaxf(m, s_m[w]);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < RT_MAXV4 * 4; ++i) sum += expf(v[i] - m);   // exp(-inf) = 0 for the padding
   sum = warp_sum(sum);
-  if (lane == 0) s_red[warp] = sum;
+  if (lane == 0) s_s[warp] = sum;
   __syncthreads();
   sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < NW; ++w) sum += s_red[w];
-  // candidate scores
+  for (int w = 0; w < NW; ++w) sum += s_s[w];
+  // ---- candidate scores (pipeline.py:117,122 in prob mode; the same ordering in the log domain otherwise)
   if (st.prob_mode) {
 #pragma unroll
-    for (int i = 0; i < RT_MAXV4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = (i * THREADS + tid) * 4 + j;
-        v[4 * i + j] = (e < V) ? (expf(v[4 * i + j] - m) / sum) * score : -INFINITY;   // pipeline.py:117,122
-      }
+    for (int i = 0; i < RT_MAXV4 * 4; ++i) v[i] = (expf(v[i] - m) / sum) * score;
   } else {
     const float lse = m + logf(sum);
 #pragma unroll
-    for (int i = 0; i < RT_MAXV4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = (i * THREADS + tid) * 4 + j;
-        v[4 * i + j] = (e < V) ? score + (v[4 * i + j] - lse) : -INFINITY;
-      }
+    for (int i = 0; i < RT_MAXV4 * 4; ++i) v[i] = score + (v[i] - lse);
   }
-  // warp-local top-N: N shuffle-only rounds
+#pragma unroll
+  for (int i = 0; i < RT_MAXV4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((i * THREADS + tid) * 4 + j >= V) v[4 * i + j] = -INFINITY;
+  // ---- per-warp top-N: the lane that owns the round's winner is the only one that rescans
   unsigned long long taken = 0ull;
-  for (int k = 0; k < N; ++k) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
+  float bv;
+  int bi;
+  auto rescan = [&]() {
+    bv = -INFINITY;
+    bi = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < RT_MAXV4; ++i)
 #pragma unroll
@@ -145,18 +148,24 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
           bi = e;
         }
       }
-    warp_argmax(bv, bi);
+  };
+  rescan();
+  for (int k = 0; k < N; ++k) {
+    float wv = bv;
+    int wi = bi;
+    warp_argmax(wv, wi);
     if (lane == 0) {
-      s_cv[warp * 32 + k] = bv;
-      s_ci[warp * 32 + k] = bi;
+      s_cv[warp * 32 + k] = wv;
+      s_ci[warp * 32 + k] = wi;
     }
-    if (bi != 0x7fffffff) {
-      const int slot4 = bi >> 2;                        // which float4 of the row
-      if (slot4 % THREADS == tid) taken |= 1ull << (4 * (slot4 / THREADS) + (bi & 3));
+    if (wi == bi && bi != 0x7fffffff) {                    // element indices are unique -> exactly one owner
+      const int slot4 = bi >> 2;
+      taken |= 1ull << (4 * (slot4 / THREADS) + (bi & 3));
+      rescan();
     }
   }
   __syncthreads();
-  // warp 0 merges the NW*N survivors (lane holds up to NW of them; N <= 32)
+  // ---- warp 0 merges the NW*N survivors (lane k holds the k-th candidate of every warp; N <= 32)
   if (warp == 0) {
     float cv[NW];
     int ci[NW];
@@ -167,56 +176,40 @@ __global__ void __launch_bounds__(THREADS) k_beam_rowtopk(BeamState st, const fl
       ci[w] = ok ? s_ci[w * 32 + lane] : 0x7fffffff;
     }
     for (int k = 0; k < N; ++k) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
+      float b2 = -INFINITY;
+      int i2 = 0x7fffffff;
 #pragma unroll
       for (int w = 0; w < NW; ++w)
-        if (ci[w] != 0x7fffffff && better(cv[w], ci[w], bv, bi)) {
-          bv = cv[w];
-          bi = ci[w];
+        if (ci[w] != 0x7fffffff && better(cv[w], ci[w], b2, i2)) {
+          b2 = cv[w];
+          i2 = ci[w];
         }
-      warp_argmax(bv, bi);
+      warp_argmax(b2, i2);
 #pragma unroll
       for (int w = 0; w < NW; ++w)
-        if (ci[w] == bi) ci[w] = 0x7fffffff;            // indices are unique within a row -> exactly one owner
+        if (ci[w] == i2) ci[w] = 0x7fffffff;
       if (lane == 0) {
-        st.cand_val[(size_t)row * N + k] = bv;
-        st.cand_idx[(size_t)row * N + k] = bi;
+        st.cand_val[(size_t)row * N + k] = b2;
+        st.cand_idx[(size_t)row * N + k] = i2;
       }
     }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();                                      // candidates visible before the image counter moves
+      s_last = (atomicAdd(st.img_count + row / N, 1) == N - 1);
+    }
   }
-}
-int launch_beam_rowtopk(const BeamState& st, const float* logits, int ld, cudaStream_t s) {
-  if (512 * RT_MAXV4 * 4 < st.V) {
-    set_last_error("beam_rowtopk: vocabulary too large (max 24576)");
-    return 1;
-  }
-  if (st.N > 32 || (ld & 3)) {
-    set_last_error("beam_rowtopk: beam width must be <= 32 and logits ld a multiple of 4");
-    return 1;
-  }
-  if (256 * RT_MAXV4 * 4 >= st.V)
-    FPNMT_CUDA_OK(launch_k(k_beam_rowtopk<256>, dim3(st.B * st.N), dim3(256), 0, s, st, logits, ld));
-  else
-    FPNMT_CUDA_OK(launch_k(k_beam_rowtopk<512>, dim3(st.B * st.N), dim3(512), 0, s, st, logits, ld));
-  return 0;
-}
+  __syncthreads();
+  if (!s_last) return;
 
-// Phase 2.  One block per image: warp 0 selects the N best of the N x N candidates (registers + shuffles), all warps
-// then copy the parent sequences / ancestry rows.
-constexpr int MERGE_WARPS = 8;
-__global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
-  __shared__ int s_parent[32], s_token[32];
-  pdl_launch();
-  pdl_wait();
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = st.N, V = st.V, T = st.T;
-  const int t = *st.step;
+  // =================================================================== phase 2: this block closes image b
+  __threadfence();
+  const int b = row / N;
   const int cur = t & 1, nxt = cur ^ 1;
   const int NN = N * N;
   const int rows0 = b * N;
   if (warp == 0) {
-    // lane holds candidates lane, lane+32, ... (at most 32 for N <= 32)
+    st.img_count[b] = 0;                                    // re-armed for the next step
     float cv[32];
     int cf[32];
 #pragma unroll
@@ -225,9 +218,9 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
       cv[s] = -INFINITY;
       cf[s] = 0x7fffffff;
       if (c < NN) {
-        const int tok = st.cand_idx[(size_t)rows0 * N + c];
+        const int tok = __ldcg(st.cand_idx + (size_t)rows0 * N + c);
         if (tok != 0x7fffffff) {
-          cv[s] = st.cand_val[(size_t)rows0 * N + c];
+          cv[s] = __ldcg(st.cand_val + (size_t)rows0 * N + c);
           cf[s] = (c / N) * V + tok;                               // flat index over the N x V candidates
         }
       }
@@ -236,26 +229,26 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
     int my_parent = 0, my_token = 0;
     float my_score = 0.f;
     for (int k = 0; k < N; ++k) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
+      float b2 = -INFINITY;
+      int i2 = 0x7fffffff;
 #pragma unroll
       for (int s = 0; s < 32; ++s) {
-        if (cf[s] != 0x7fffffff && better(cv[s], cf[s], bv, bi)) {
-          bv = cv[s];
-          bi = cf[s];
+        if (cf[s] != 0x7fffffff && better(cv[s], cf[s], b2, i2)) {
+          b2 = cv[s];
+          i2 = cf[s];
         }
         if (32 * (s + 1) >= NN) break;
       }
-      warp_argmax(bv, bi);
+      warp_argmax(b2, i2);
 #pragma unroll
       for (int s = 0; s < 32; ++s) {
-        if (cf[s] == bi) cf[s] = 0x7fffffff;
+        if (cf[s] == i2) cf[s] = 0x7fffffff;
         if (32 * (s + 1) >= NN) break;
       }
       if (lane == k) {
-        my_parent = bi / V;                                          // pipeline.py:130
-        my_token = bi - my_parent * V;                               // pipeline.py:131
-        my_score = bv;
+        my_parent = i2 / V;                                          // pipeline.py:130
+        my_token = i2 - my_parent * V;                               // pipeline.py:131
+        my_score = b2;
       }
     }
     if (lane < N) {                                                  // lanes 0..N-1 hold the new beams in rank order
@@ -269,7 +262,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
     if (lane == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = my_score;
   }
   __syncthreads();
-  for (int n = warp; n < N; n += MERGE_WARPS) {
+  for (int n = warp; n < N; n += NW) {
     const int par = s_parent[n], tok = s_token[n];
     const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
     int* dseq = st.seq[nxt] + (size_t)(rows0 + n) * (T + 1);
@@ -280,6 +273,19 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
     if (lane == 0) {
       dseq[t + 1] = tok;
       danc[t] = rows0 + par;
+    }
+  }
+  // next step's decoder input: x[row] = embedding[token] + pos[t + 1]   (transformer.py:326-329)
+  if (em.emb && t + 1 < T) {
+    const int groups = em.D / 8;
+    for (int i = tid; i < N * groups; i += THREADS) {
+      const int n = i / groups, g = i % groups;
+      const float* ep = em.emb + (size_t)s_token[n] * em.D + g * 8;
+      const float* pp = em.pos + (size_t)(t + 1) * em.D + g * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(ep), a1 = *reinterpret_cast<const float4*>(ep + 4);
+      const float4 p0 = *reinterpret_cast<const float4*>(pp), p1 = *reinterpret_cast<const float4*>(pp + 4);
+      const float o[8] = {a0.x + p0.x, a0.y + p0.y, a0.z + p0.z, a0.w + p0.w, a1.x + p1.x, a1.y + p1.y, a1.z + p1.z, a1.w + p1.w};
+      st_act8(em.x, (size_t)(rows0 + n), g * 8, o);
     }
   }
   __syncthreads();
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
         atomicAdd(st.n_done, 1);
       }
     }
-    // last block to finish advances the step counter
+    // last image to finish advances the step counter
     if (lane == 0) {
       __threadfence();
       const int prev = atomicAdd(st.n_done + 1, 1);
@@ -308,8 +314,19 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_beam_merge(BeamState st) {
     }
   }
 }
-int launch_beam_merge(const BeamState& st, cudaStream_t s) {
-  FPNMT_CUDA_OK(launch_k(k_beam_merge, dim3(st.B), dim3(MERGE_WARPS * 32), 0, s, st));
+int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s) {
+  if (512 * RT_MAXV4 * 4 < st.V) {
+    set_last_error("beam_step: vocabulary too large (max 24576)");
+    return 1;
+  }
+  if (st.N > 32 || (ld & 3)) {
+    set_last_error("beam_step: beam width must be <= 32 and logits ld a multiple of 4");
+    return 1;
+  }
+  if (256 * RT_MAXV4 * 4 >= st.V)
+    FPNMT_CUDA_OK(launch_k(k_beam_step<256>, dim3(st.B * st.N), dim3(256), 0, s, st, logits, ld, em));
+  else
+    FPNMT_CUDA_OK(launch_k(k_beam_step<512>, dim3(st.B * st.N), dim3(512), 0, s, st, logits, ld, em));
   return 0;
 }
 

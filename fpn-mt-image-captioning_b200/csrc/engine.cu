@@ -62,6 +62,8 @@ int Engine::init() {
   if (prop.major != 10) return fail(FPNMT_ERR_CUDA, "this library contains sm_100a code only; device is not Blackwell");
   num_sms_ = prop.multiProcessorCount;
   RC(igemm_set_attributes());
+  RC(tgemm_set_attributes());
+  if (const char* e = getenv("FPNMT_TGEMM")) use_tgemm_ = !(e[0] == '0');
   FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
   FPNMT_CUDA_OK(cudaMallocHost(&h_pinned_, 64));
   return 0;
@@ -299,6 +301,32 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   o.bytes = (double)in.pixels() * in.a.C * esz + (double)gw.Cout * gw.K * esz +
             (double)in.pixels() * gw.Cout * (out_f32 ? 4.0 : esz) + (res ? (double)res->pixels() * gw.Cout * esz : 0.0);
   o.run = [op](cudaStream_t s) { return igemm_launch(op, s); };
+  prog.push_back(std::move(o));
+  return 0;
+}
+
+int Engine::add_dense(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int act, const Tensor* res,
+                      const Tensor& out, float* out_f32, int ld_f32, const float* gamma, const float* beta) {
+  if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
+  const int R = (int)in.pixels();
+  TgemmOp op;
+  RC(make_tgemm_op(&op, R, in.a, gw.w, gw.Cout, gw.K, split_, gw.bias, act, out.a, out_f32, ld_f32, res ? &res->a : nullptr,
+                   gamma, beta, 1e-6f, num_sms_));
+  if (const char* dn = getenv("FPNMT_DBG_OP")) {
+    if (name == dn) {
+      dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
+      cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+      op.p.dbg = dbg_buf_;
+    }
+  }
+  Op o;
+  o.name = name;
+  o.kind = "tgemm";
+  o.flops = op.flops * (split_ ? 3.0 : 1.0);
+  const double esz = split_ ? 4.0 : 2.0;
+  o.bytes = (double)R * gw.K * esz + (double)gw.Cout * gw.K * esz + (double)R * gw.Cout * (out_f32 ? 4.0 : esz) +
+            (res ? (double)R * gw.Cout * esz : 0.0);
+  o.run = [op](cudaStream_t s) { return tgemm_launch(op, s); };
   prog.push_back(std::move(o));
   return 0;
 }
@@ -739,6 +767,8 @@ int Engine::build_decoder() {
   bs_.step = (int*)dalloc(16);
   bs_.done = (int*)dalloc((size_t)B * 4);
   bs_.n_done = (int*)dalloc(16);
+  bs_.img_count = (int*)dalloc((size_t)B * 4);
+  FPNMT_CUDA_OK(cudaMemset(bs_.img_count, 0, (size_t)B * 4));
   bs_.out_ids = (int*)dalloc((size_t)B * T * 4);
   bs_.out_len = (int*)dalloc((size_t)B * 4);
   bs_.cand_val = (float*)dalloc((size_t)R * N * 4);
@@ -780,12 +810,14 @@ int Engine::build_decoder() {
 
     Tensor x = rows_act(R, D);
     const BeamState bs = bs_;
+    // step 0 input (embedding of <start> + pos[0]); later steps' inputs are written by the beam kernel
     {
       Act xa = x.a;
       const int* tok = bs_.last_tok;
       const int* step = bs_.step;
-      step_prog_.push_back(ew_op("embed_pos", [=](cudaStream_t s) { return launch_embed_pos(tok, d_emb, d_pos, step, R, D, xa, s); }, (double)R * D * 6));
+      embed_prog_.push_back(ew_op("embed_pos", [=](cudaStream_t s) { return launch_embed_pos(tok, d_emb, d_pos, step, R, D, xa, s); }, (double)R * D * 6));
     }
+    beam_embed_ = BeamEmbed{d_emb, d_pos, x.a, D};
     Tensor none;
     for (int l = 0; l < L; ++l) {
       const std::string d = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l);
@@ -804,7 +836,21 @@ int Engine::build_decoder() {
              out2 = rows_act(R, D), hdn = rows_act(R, FF), out3 = rows_act(R, D);
       Tensor kc = rows_act(R * T, D), vc = rows_act(R * T, D);
       float* y = (float*)dalloc((size_t)R * D * 4);
-      RC(add_conv(step_prog_, ln + "_qkv", x, gqkv, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, qkv));
+      // Dense layers of the step: skinny-row tgemm (weights prefetched before the grid dependency, LayerNorm fused into
+      // the epilogue by a 4-CTA cluster) or, with FPNMT_TGEMM=0, the generic igemm + separate LayerNorm kernels.
+      auto dense = [&](const std::string& nm, const Tensor& in, const GemmW& g, int act, const Tensor& out) -> int {
+        if (use_tgemm_) return add_dense(step_prog_, nm, in, g, act, nullptr, out);
+        return add_conv(step_prog_, nm, in, g, 1, 1, 0, 0, act, RES_NONE, nullptr, out);
+      };
+      auto dense_res_ln = [&](const std::string& nm, const std::string& lnn2, const Tensor& in, const GemmW& g, const Tensor& res,
+                              float* gam, float* bet, const Tensor& out) -> int {
+        if (use_tgemm_) return add_dense(step_prog_, nm + "+ln", in, g, ACT_NONE, &res, out, nullptr, 0, gam, bet);
+        RC(add_conv(step_prog_, nm, in, g, 1, 1, 0, 0, ACT_NONE, RES_SAME, &res, none, y, D));
+        Act oa = out.a;
+        step_prog_.push_back(ew_op(lnn2, [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, gam, bet, 1e-6f, oa, s); }, (double)R * D * 6));
+        return 0;
+      };
+      RC(dense(ln + "_qkv", x, gqkv, ACT_NONE, qkv));
       {
         Act qa = qkv.a, ka = kc.a, va = vc.a, oa = att.a;
         const int* ancp = anc;
@@ -813,45 +859,31 @@ int Engine::build_decoder() {
                      (double)R * (T / 2) * 2 * D * 2, "attention");
         step_prog_.push_back(std::move(o));
       }
-      RC(add_conv(step_prog_, ln + "_o1+res", att, go1, 1, 1, 0, 0, ACT_NONE, RES_SAME, &x, none, y, D));
-      {
-        Act oa = out1.a;
-        float *g = lnp[0], *b = lnp[1];
-        step_prog_.push_back(ew_op(ln + "_ln1", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
-      }
-      RC(add_conv(step_prog_, ln + "_q2", out1, gq2, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, q2));
+      RC(dense_res_ln(ln + "_o1+res", ln + "_ln1", att, go1, x, lnp[0], lnp[1], out1));
+      RC(dense(ln + "_q2", out1, gq2, ACT_NONE, q2));
       {
         Act qa = q2.a, ka = ckv.a, oa = att2.a;
         const int kcx = l * 2 * D, vcx = l * 2 * D + D, tk = n_base_;
         step_prog_.push_back(ew_op(ln + "_cross_attn", [=](cudaStream_t s) { return launch_dec_cross_attention(qa, ka, kcx, vcx, R, N, tk, H, oa, s); },
                                    (double)B * tk * 2 * D * 2, "attention"));
       }
-      RC(add_conv(step_prog_, ln + "_o2+res", att2, go2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out1, none, y, D));
-      {
-        Act oa = out2.a;
-        float *g = lnp[2], *b = lnp[3];
-        step_prog_.push_back(ew_op(ln + "_ln2", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
-      }
-      RC(add_conv(step_prog_, ln + "_ffn1", out2, g1, 1, 1, 0, 0, ACT_LEAKY, RES_NONE, nullptr, hdn));
-      RC(add_conv(step_prog_, ln + "_ffn2+res", hdn, g2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out2, none, y, D));
-      {
-        Act oa = out3.a;
-        float *g = lnp[4], *b = lnp[5];
-        step_prog_.push_back(ew_op(ln + "_ln3", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g, b, 1e-6f, oa, s); }, (double)R * D * 6));
-      }
+      RC(dense_res_ln(ln + "_o2+res", ln + "_ln2", att2, go2, out1, lnp[2], lnp[3], out2));
+      RC(dense(ln + "_ffn1", out2, g1, ACT_LEAKY, hdn));
+      RC(dense_res_ln(ln + "_ffn2+res", ln + "_ln3", hdn, g2, out2, lnp[4], lnp[5], out3));
       x = out3;
     }
     GemmW gf;
     RC(prep_dense_cat({std::string(TR) + "/final_layer"}, &gf));
     float* lg = logits_;
-    RC(add_conv(step_prog_, "final_layer", x, gf, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, none, lg, V));
-    step_forced_prog_ = step_prog_;   // shared prefix; the tails differ
+    if (use_tgemm_) RC(add_dense(step_prog_, "final_layer", x, gf, ACT_NONE, nullptr, none, lg, V));
+    else RC(add_conv(step_prog_, "final_layer", x, gf, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, none, lg, V));
+    step_forced_prog_ = embed_prog_;   // teacher forcing: embed the forced token, then the shared layer stack
+    step_forced_prog_.insert(step_forced_prog_.end(), step_prog_.begin(), step_prog_.end());
     {
-      Op o = ew_op("beam_rowtopk", [=](cudaStream_t s) { return launch_beam_rowtopk(bs, lg, V, s); }, (double)R * V * 4, "beam");
+      const BeamEmbed em = beam_embed_;
+      Op o = ew_op("beam_step", [=](cudaStream_t s) { return launch_beam_step(bs, lg, V, em, s); }, (double)R * V * 4 + (double)R * (T + 1) * 8, "beam");
+      o.idempotent = false;
       step_prog_.push_back(std::move(o));
-      Op m = ew_op("beam_merge", [=](cudaStream_t s) { return launch_beam_merge(bs, s); }, (double)R * (T + 1) * 8, "beam");
-      m.idempotent = false;
-      step_prog_.push_back(std::move(m));
     }
   }
   return 0;
@@ -1013,9 +1045,8 @@ int Engine::beam_step(const float* logits, const float* scores_in, int32_t* pare
   const int R = cfg_.batch * cfg_.beam;
   RC(launch_beam_init(bs_, 0, s));
   FPNMT_CUDA_OK(cudaMemcpyAsync(bs_.score[0], scores_in, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  RC(launch_beam_rowtopk(bs_, logits, cfg_.vocab, s));
-  RC(launch_beam_merge(bs_, s));
-  launches += 3;
+  RC(launch_beam_step(bs_, logits, cfg_.vocab, BeamEmbed{nullptr, nullptr, Act{nullptr, 0, 0, 0}, 0}, s));
+  launches += 2;
   FPNMT_CUDA_OK(cudaMemcpyAsync(parent, bs_.parent_out, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
   FPNMT_CUDA_OK(cudaMemcpyAsync(token, bs_.token_out, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
   FPNMT_CUDA_OK(cudaMemcpyAsync(scores_out, bs_.score[1], (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
@@ -1029,6 +1060,7 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
   RC(launch_beam_init(bs_, cfg_.true_beam, s));
   launches += 1;
   RC(run_program(dec_init_prog_, s));
+  RC(run_program(embed_prog_, s));
   if (cfg_.use_graphs && !step_graph_) RC(capture(step_prog_, &step_graph_));
   for (int t = 0; t < T; ++t) {
     RC(launch_prog(step_prog_, step_graph_, s));
@@ -1106,6 +1138,7 @@ int Engine::profile(int iters, char* buf, size_t cap) {
   cudaStream_t s = cap_stream_;
   RC(launch_beam_init(bs_, cfg_.true_beam, s));
   RC(run_program(dec_init_prog_, s));
+  RC(run_program(embed_prog_, s));
   const int warm = cfg_.max_len / 2;
   for (int t = 0; t < warm; ++t) RC(run_program(step_prog_, s));
   RC(profile_program(dec_init_prog_, iters, json, "decode_init"));
@@ -1118,7 +1151,7 @@ int Engine::profile(int iters, char* buf, size_t cap) {
   if (dbg_buf_) {   // FPNMT_DBG_OP timeline of the last 8 instances (ns relative to each instance's entry)
     long long h[16 * 9];
     cudaMemcpy(h, dbg_buf_, sizeof h, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[fpnmt dbg] %lld instances; stamps: entry setup pdl_wait first_full mma_issued tfull res_ready epi_done end\n", h[0]);
+    fprintf(stderr, "[fpnmt dbg] %lld instances; stamps: entry setup pdl_wait first_full mma_issued tfull epi_chunk0 epi_chunk1 end\n", h[0]);
     for (int i = 0; i < 8; ++i) {
       const long long* t = h + 16 + i * 16;
       fprintf(stderr, "[fpnmt dbg] inst slot %d entry@%lld:", i, t[0]);

@@ -10,6 +10,7 @@
 #include "igemm.cuh"
 #include "kernels.cuh"
 #include "tensormap.cuh"
+#include "tgemm.cuh"
 
 namespace fpnmt {
 
@@ -71,7 +72,8 @@ class Engine {
   std::map<std::string, Tensor> taps_;
 
   // programs
-  Program cnn_prog_, enc_prog_, dec_init_prog_, step_prog_, step_forced_prog_;
+  Program cnn_prog_, enc_prog_, dec_init_prog_, embed_prog_, step_prog_, step_forced_prog_;
+  BeamEmbed beam_embed_{};
   cudaGraphExec_t cnn_graph_ = nullptr, enc_graph_ = nullptr, step_graph_ = nullptr;
   cudaStream_t cap_stream_ = nullptr;
 
@@ -109,6 +111,11 @@ class Engine {
   int add_conv(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int kh, int kw, int pad_t,
                int pad_l, int act, int res_mode, const Tensor* res, const Tensor& out, float* out_f32 = nullptr,
                int ld_f32 = 0);
+  // skinny-row Dense (tgemm): out = act(in @ W + b [+ res]) or LayerNorm(in @ W + b + res) when gamma != nullptr
+  int add_dense(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int act, const Tensor* res,
+                const Tensor& out, float* out_f32 = nullptr, int ld_f32 = 0, const float* gamma = nullptr,
+                const float* beta = nullptr);
+  bool use_tgemm_ = true;                 // FPNMT_TGEMM=0 routes the decoder GEMMs through igemm + separate LayerNorm
   int build_stem_resnet_like(Program& p, const std::string& conv_key, const std::string& bn_key, float eps, Tensor* out);
   int build_resnet50(Program& p, Tensor c[3]);
   int build_mobilenetv2(Program& p, Tensor c[3]);

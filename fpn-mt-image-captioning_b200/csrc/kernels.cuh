@@ -57,7 +57,8 @@ struct BeamState {
   int* last_tok;             // [B*N] token fed to the next step
   int* step;                 // device scalar: current step t (0-based)
   int* done;                 // [B] 1 once the image's top beam has emitted <end>
-  int* n_done;               // [2]: number of finished images, block-completion counter
+  int* n_done;               // [2]: number of finished images, image-completion counter
+  int* img_count;            // [B] rows of the image whose candidates are ready (elects the block that merges)
   int* out_ids;              // [B][T]
   int* out_len;              // [B]
   float* cand_val;           // [B*N][N] per-row candidates (phase 1 -> phase 2)
@@ -68,11 +69,17 @@ struct BeamState {
 };
 // true_beam = 0 reproduces the reference (all beams start identical, pipeline.py:101-102); 1 starts beams 1..N-1 dead
 int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s);
-// phase 1: per (image, beam) row softmax statistics + candidate scores + row-local top-N
-int launch_beam_rowtopk(const BeamState& st, const float* logits, int ld, cudaStream_t s);
-// phase 2: merge N x N candidates per image, emit parents/tokens/scores, reorder sequences + ancestry,
-// handle <end>, advance the step counter.  Buffers are double-buffered on (step & 1).
-int launch_beam_merge(const BeamState& st, cudaStream_t s);
+// Next-step decoder input written by the beam kernel: x[row] = emb[token] + pos[step + 1] (emb == nullptr: skip).
+struct BeamEmbed {
+  const float* emb;          // [V][D] fp32
+  const float* pos;          // [T][D] fp32
+  Act x;                     // [B*N][D]
+  int D;
+};
+// One beam-search step on fp32 logits [B*N][ld]: row softmax statistics + candidate scores + row-local top-N, then
+// (last block of each image) merge N x N candidates, emit parents/tokens/scores, reorder sequences + ancestry, handle
+// <end>, write the next decoder input, advance the step counter.  Buffers are double-buffered on (step & 1).
+int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s);
 // Physical KV reorder variant: dst[row] = src[parent-mapped row] for positions <= step (bandwidth kernel).
 int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
                      cudaStream_t s);

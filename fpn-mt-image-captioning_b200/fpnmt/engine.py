@@ -205,3 +205,24 @@ def conv2d(x: torch.Tensor, kernel_hwio: np.ndarray, bias: Optional[np.ndarray] 
                                    None if r is None else r.data_ptr(), res_mode, out.data_ptr(), force_bn,
                                    _stream_ptr(dev)))
     return out
+
+
+def dense(x: torch.Tensor, kernel: np.ndarray, bias: Optional[np.ndarray] = None, act: int = 0,
+          residual: Optional[torch.Tensor] = None, gamma: Optional[np.ndarray] = None, beta: Optional[np.ndarray] = None,
+          eps: float = 1e-6, precision: str = "bf16", force_bn: int = 0) -> torch.Tensor:
+    """Stand-alone skinny-row Dense (+ residual + LayerNorm) through the C ABI — used by the kernel parity tests."""
+    lib = _lib.load()
+    dev = x.device
+    x = x.to(torch.float32).contiguous()
+    r, k = x.shape
+    kn = np.ascontiguousarray(kernel, dtype=np.float32)
+    f = kn.shape[1]
+    host = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    b, g, be = host(bias), host(gamma), host(beta)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    res = None if residual is None else residual.to(torch.float32).contiguous()
+    out = torch.empty((r, f), dtype=torch.float32, device=dev)
+    _lib.check(lib.fpnmt_op_dense(dev.index or 0, _lib.PREC_IDS[precision], x.data_ptr(), r, k, ptr(kn), f, ptr(b), act,
+                                  None if res is None else res.data_ptr(), ptr(g), ptr(be), eps, out.data_ptr(), force_bn,
+                                  _stream_ptr(dev)))
+    return out

@@ -138,6 +138,15 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
                     int kh, int kw, int Cout, int pad_top, int pad_left, const float* bias, int act,
                     const float* residual, int res_mode, float* out, int force_bn, void* stream);
 
+/* out[r, f] = epilogue( x[r, :] @ kernel[:, f] + bias[f] [+ residual[r, f]] ) with the skinny-row Dense kernel of the
+ * decoder step (tf.keras.layers.Dense, models/transformer.py:117-122, 165-168, 211-214, 357): x DEVICE float32 [R, K];
+ * kernel HOST float32 (K, F) Keras layout; bias HOST [F] or NULL; residual DEVICE float32 [R, F] or NULL; out DEVICE
+ * float32 [R, F].  gamma/beta HOST [F] != NULL (F must be 512): the epilogue is LayerNormalization(epsilon=eps) of
+ * (dense + residual) (models/transformer.py:192,198,230,235,241), computed by a 4-CTA cluster. act as fpnmt_op_conv2d. */
+FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, int K, const float* kernel, int F,
+                   const float* bias, int act, const float* residual, const float* gamma, const float* beta, float eps,
+                   float* out, int force_bn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ import torch
 from .backbones import backbone_forward
 from .ops import W, bn_calibration, nhwc_to_nchw
 
-__all__ = ["TEST_GAINS", "test_weights", "test_images"]
+__all__ = ["TEST_GAINS", "test_weights", "test_images", "bf16_conv_emulation"]
 
 TEST_GAINS = {"/model/conv2d_4": 48.0, "/model/conv2d_5": 48.0, "pyramid_regression": 3.0, "pyramid_classification": 3.0,
               "final_layer": 6.0, "decoder/embedding": 20.0}
@@ -53,3 +53,30 @@ def test_images(n: int, size: int = 256, seed: int = 1) -> torch.Tensor:
 
 
 test_images.__test__ = False
+
+
+class bf16_conv_emulation:
+    """Context manager: every convolution of the oracle rounds its input, kernel and output to bfloat16 (fp32
+    accumulation) — the arithmetic of the engine's BF16 fast mode.  Used to state that mode's stage tolerance relative
+    to what bf16 rounding alone does to a random-init BatchNorm network (perturbations grow ~1.2x per layer)."""
+
+    def __enter__(self):
+        from . import backbones, model, ops
+        self._mods = (ops, backbones, model)
+        self._saved = [(m, n, getattr(m, n)) for m in self._mods for n in ("conv2d", "depthwise_conv2d") if hasattr(m, n)]
+        oc, od = ops.conv2d, ops.depthwise_conv2d
+        r = lambda t: t.to(torch.bfloat16).to(t.dtype)
+
+        def conv2d(x, k, b=None, *a, **kw):
+            return r(oc(r(x), r(k), b, *a, **kw))
+
+        def depthwise_conv2d(x, k, *a, **kw):
+            return r(od(r(x), k, *a, **kw))
+        for m, n, _ in self._saved:
+            setattr(m, n, conv2d if n == "conv2d" else depthwise_conv2d)
+        return self
+
+    def __exit__(self, *a):
+        for m, n, f in self._saved:
+            setattr(m, n, f)
+        return False

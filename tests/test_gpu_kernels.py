@@ -137,3 +137,51 @@ def test_beam_step_bit_exact(beam_engines, mode, trial):
         assert np.allclose(sc[sl], s, rtol=1e-5, atol=1e-6)
     if trial == "underflow":
         assert tok[:N].tolist() == [0, 1, 2, 3] and par[:N].tolist() == [0, 0, 0, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# skinny-row Dense kernel of the decoder step (tgemm): plain and cluster-LayerNorm epilogues
+DENSE_CASES = [
+    # name, R, K, F, act, residual, layernorm, force_bn
+    ("o_proj_512", 512, 512, 512, 0, False, False, 0),
+    ("qkv_1536_bn64", 512, 512, 1536, 0, False, False, 0),
+    ("ffn1_leaky_2048", 512, 512, 2048, 2, False, False, 0),
+    ("ffn2_k2048_res", 512, 2048, 512, 0, True, False, 0),
+    ("vocab_1000_ragged_features", 192, 512, 1000, 0, False, False, 0),
+    ("ragged_rows_100_bn32", 100, 512, 512, 1, True, False, 32),
+    ("ragged_rows_100_bn64", 100, 512, 256, 0, False, False, 64),
+    ("multi_rowtile_stationary", 1024, 512, 10000, 0, False, False, 0),
+    ("ln_o_proj", 512, 512, 512, 0, True, True, 0),
+    ("ln_ffn2_k2048", 512, 2048, 512, 0, True, True, 0),
+    ("ln_ragged_rows_40", 40, 512, 512, 0, True, True, 0),
+    ("ln_no_residual", 64, 512, 512, 0, False, True, 0),
+]
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_tgemm_dense(case, prec, tol):
+    from fpnmt.engine import dense
+    name, R, K, Fo, act, has_res, ln, fbn = case
+    g = torch.Generator().manual_seed(abs(hash(name)) % (2 ** 31))
+    x = torch.randn(R, K, generator=g)
+    k = (torch.randn(K, Fo, generator=g) / np.sqrt(K)).numpy()
+    b = torch.randn(Fo, generator=g).numpy() * 0.5
+    res = torch.randn(R, Fo, generator=g) if has_res else None
+    gam = (torch.rand(Fo, generator=g) + 0.5).numpy() if ln else None
+    bet = torch.randn(Fo, generator=g).numpy() if ln else None
+    y = dense(x.cuda(), k, b, act, None if res is None else res.cuda(), gam, bet, 1e-6, prec, fbn).cpu()
+    ref = x.double() @ torch.from_numpy(k).double() + torch.from_numpy(b).double()
+    if has_res:
+        ref = ref + res.double()
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.where(ref >= 0, ref, 0.2 * ref)
+    if ln:
+        mean = ref.mean(-1, keepdim=True)
+        var = ((ref - mean) ** 2).mean(-1, keepdim=True)
+        ref = (ref - mean) / torch.sqrt(var + 1e-6) * torch.from_numpy(gam).double() + torch.from_numpy(bet).double()
+    err = float((y.double() - ref).norm() / ref.norm())
+    assert err < tol, (name, prec, err)
+    assert torch.isfinite(y).all()
