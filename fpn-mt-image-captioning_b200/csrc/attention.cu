@@ -3,6 +3,8 @@
 //                         single pass with online softmax; one block per (image, head), 4 queries per warp.
 //   dec_self_attention  : one new query per (row, head) against the KV cache through the beam-ancestry table.
 //   dec_cross_attention : one query per (row, head) against the 16 memory tokens of the row's image.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace fpnmt {
@@ -104,6 +106,207 @@ __global__ void __launch_bounds__(128) k_enc_attention(Act q, int q_col, Act kv,
     }
   }
 }
+// ---------------------------------------------------------------------------------------- encoder, tensor-core path
+// bf16 mode.  One block (4 warps) per (image, head): the <= 16 baseline queries form exactly one m16 MMA row block, so
+// S = Q K^T and O = P V run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) flash-style: each warp walks the key axis
+// in tiles of 64 keys (its K and V tiles staged in swizzled shared memory by 16-byte cp.async, fragments read with
+// ldmatrix / ldmatrix.trans), keeps online-softmax statistics in registers, and the four warps' partial (m, l, O) are
+// merged through shared memory at the end.  (tcgen05 needs M >= 64 rows per tile; 16 queries per head do not fill it.)
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+constexpr int EA_WARPS = 4;
+constexpr int EA_TILE = 64;                       // keys per tile
+constexpr int EA_TILE_BYTES = EA_TILE * DH * 2;   // 8 KB
+constexpr int EA_SMEM = EA_WARPS * 2 * EA_TILE_BYTES + EA_WARPS * 16 * 2 * 4;
+
+__global__ void __launch_bounds__(EA_WARPS * 32) k_enc_attention_mma(Act q, int q_col, Act kv, int k_col, int v_col, int Tq,
+                                                                    int Tk, Act out, int out_col) {
+  extern __shared__ __align__(128) uint8_t ea_smem[];
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint8_t* sK = ea_smem + warp * 2 * EA_TILE_BYTES;
+  uint8_t* sV = sK + EA_TILE_BYTES;
+  float* sM = reinterpret_cast<float*>(ea_smem + EA_WARPS * 2 * EA_TILE_BYTES);   // [EA_WARPS][16]
+  float* sL = sM + EA_WARPS * 16;
+  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+
+  // Q fragments (rows g and g+8 of the 16-query block; 4 k-steps of 16 dims)
+  uint32_t qa[4][4];
+  {
+    const bf16* q0 = q.p + (size_t)(b * Tq + g) * q.ld + q_col + h * DH;
+    const bf16* q1 = q0 + (size_t)8 * q.ld;
+    const bool ok0 = g < Tq, ok1 = g + 8 < Tq;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int c = s4 * 16 + 2 * t;
+      qa[s4][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+      qa[s4][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+      qa[s4][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+      qa[s4][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
+    }
+  }
+  float o_acc[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o_acc[d][i] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // rows g and g+8 (this thread's quad share)
+
+  const int ntiles = (Tk + EA_TILE - 1) / EA_TILE;
+  for (int tile = warp; tile < ntiles; tile += EA_WARPS) {
+    const int key0 = tile * EA_TILE;
+    // ---- stage K and V tiles: 64 keys x 8 chunks of 16 B each, chunk index swizzled with (key & 7)
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int c = it * 32 + lane;
+      const int key = c >> 3, ch = c & 7;
+      const bool ok = key0 + key < Tk;
+      const bf16* src = kv.p + (size_t)(b * Tk + (ok ? key0 + key : 0)) * kv.ld + h * DH + ch * 8;
+      const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
+      cp16(sK_u + off, src + k_col, ok);
+      cp16(sV_u + off, src + v_col, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- S = Q K^T for the 64 keys (8 n-tiles of 8 keys)
+    float s_acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_acc[j][i] = 0.f;
+      const int key = 8 * j + (lane & 7);
+#pragma unroll
+      for (int sp = 0; sp < 2; ++sp) {              // two k-steps (32 dims) per ldmatrix.x4
+        uint32_t kb[4];
+        const int ch = 4 * sp + (lane >> 3);
+        ldsm_x4(kb, sK_u + key * 128 + ((ch ^ (key & 7)) << 4));
+        mma_16816(s_acc[j], qa[2 * sp], kb[0], kb[1]);
+        mma_16816(s_acc[j], qa[2 * sp + 1], kb[2], kb[3]);
+      }
+    }
+    // ---- online softmax (scale 1/sqrt(64)); keys beyond Tk are masked
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = key0 + 8 * j + 2 * t;
+      s_acc[j][0] = kk < Tk ? s_acc[j][0] * 0.125f : -INFINITY;
+      s_acc[j][1] = kk + 1 < Tk ? s_acc[j][1] * 0.125f : -INFINITY;
+      s_acc[j][2] = kk < Tk ? s_acc[j][2] * 0.125f : -INFINITY;
+      s_acc[j][3] = kk + 1 < Tk ? s_acc[j][3] * 0.125f : -INFINITY;
+      tm0 = fmaxf(tm0, fmaxf(s_acc[j][0], s_acc[j][1]));
+      tm1 = fmaxf(tm1, fmaxf(s_acc[j][2], s_acc[j][3]));
+    }
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+    const float n0 = fmaxf(m0, tm0), n1 = fmaxf(m1, tm1);
+    const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);
+    m0 = n0;
+    m1 = n1;
+    float ps0 = 0.f, ps1 = 0.f;
+    uint32_t pa[4][4];                               // P as A fragments: k-step kk covers keys 16kk .. 16kk+15
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = __expf(s_acc[j][0] - n0), p1 = __expf(s_acc[j][1] - n0);
+      const float p2 = __expf(s_acc[j][2] - n1), p3 = __expf(s_acc[j][3] - n1);
+      ps0 += p0 + p1;
+      ps1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2] = pack2(p0, p1);       // a0 / a2: row g
+      pa[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);   // a1 / a3: row g+8
+    }
+    l0 = l0 * c0 + ps0;
+    l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      o_acc[d][0] *= c0;
+      o_acc[d][1] *= c0;
+      o_acc[d][2] *= c1;
+      o_acc[d][3] *= c1;
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {              // two 8-dim n-tiles per ldmatrix.x4.trans
+        uint32_t vb[4];
+        const int mi = lane >> 3;
+        const int key = 16 * kk + (mi & 1) * 8 + (lane & 7);
+        const int ch = 2 * dp + (mi >> 1);
+        ldsm_x4_t(vb, sV_u + key * 128 + ((ch ^ (key & 7)) << 4));
+        mma_16816(o_acc[2 * dp], pa[kk], vb[0], vb[1]);
+        mma_16816(o_acc[2 * dp + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- merge the four warps: quad-reduce l, publish (m, l) and O, then every thread finishes 8 output values
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  __syncthreads();                                   // all tiles consumed: the K/V area becomes the O exchange buffer
+  float* sO = reinterpret_cast<float*>(ea_smem);     // [EA_WARPS][16][64]
+  if (t == 0) {
+    sM[warp * 16 + g] = m0;
+    sM[warp * 16 + g + 8] = m1;
+    sL[warp * 16 + g] = l0;
+    sL[warp * 16 + g + 8] = l1;
+  }
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    float* r0 = sO + (warp * 16 + g) * DH + 8 * d + 2 * t;
+    float* r1 = sO + (warp * 16 + g + 8) * DH + 8 * d + 2 * t;
+    r0[0] = o_acc[d][0];
+    r0[1] = o_acc[d][1];
+    r1[0] = o_acc[d][2];
+    r1[1] = o_acc[d][3];
+  }
+  __syncthreads();
+  {
+    const int row = threadIdx.x >> 3, d0 = (threadIdx.x & 7) * 8;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < EA_WARPS; ++w) M = fmaxf(M, sM[w * 16 + row]);
+    float L = 0.f, o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < EA_WARPS; ++w) {
+      const float mw = sM[w * 16 + row];
+      const float sc = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+      L += sL[w * 16 + row] * sc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(sO[(w * 16 + row) * DH + d0 + i], sc, o[i]);
+    }
+    if (row < Tq) {
+      const float inv = 1.f / L;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= inv;
+      st_act8(out, (size_t)b * Tq + row, out_col + h * DH + d0, o);
+    }
+  }
+}
+
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
                          int out_col, cudaStream_t s) {
   if (Tq > 16) {
@@ -111,6 +314,17 @@ int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, 
     return 1;
   }
   dim3 grid(B, heads);
+  const char* force_simt = getenv("FPNMT_ENC_ATT_SIMT");   // test hook: compare the two paths on identical inputs
+  if (!kv.lo && !q.lo && !out.lo && !(force_simt && force_simt[0] == '1')) {   // bf16 mode: tensor-core flash kernel
+    static bool attr_done = false;
+    if (!attr_done) {
+      FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+      attr_done = true;
+    }
+    FPNMT_CUDA_OK(launch_k(k_enc_attention_mma, dim3(grid), dim3(EA_WARPS * 32), (size_t)EA_SMEM, s, q, q_col, kv, k_col, v_col,
+                           Tq, Tk, out, out_col));
+    return 0;
+  }
   FPNMT_CUDA_OK(launch_k(k_enc_attention, dim3(grid), dim3(128), 0, s, q, q_col, kv, k_col, v_col, Tq, Tk, out, out_col));
   LAUNCH_CHECK();
   return 0;
@@ -121,6 +335,7 @@ int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, 
 // (broadcast reads).  Score pass: lane j owns position k0+j and reads its 128 B key row with 8 independent 16 B
 // loads (memory-level parallelism, few registers); value pass: lanes own 2 output dims and the probabilities are
 // broadcast by shuffle, loads unrolled.  `krow(pos)` maps a position to the row of the K/V views.
+template <bool SPLIT>
 __device__ __forceinline__ float dot_row64(const Act& a, size_t row, int col, const float* __restrict__ qs) {
   const bf16* p = a.p + row * (size_t)a.ld + col;
   uint4 h[8];
@@ -134,7 +349,7 @@ __device__ __forceinline__ float dot_row64(const Act& a, size_t row, int col, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc = fmaf(qs[i * 8 + j], f[j], acc);
   }
-  if (a.lo) {
+  if constexpr (SPLIT) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const uint4*>(p + a.lo + i * 8);
 #pragma unroll
@@ -148,34 +363,67 @@ __device__ __forceinline__ float dot_row64(const Act& a, size_t row, int col, co
   return acc;
 }
 
-template <typename RowFn>
-__device__ __forceinline__ void warp_attend(const float* __restrict__ qs, const Act& kc, int k_col, const Act& vc,
-                                            int v_col, int Tk, RowFn krow, int lane, float& m, float& l, float& o0,
-                                            float& o1) {
+// Value pass layout: lane = pg * 8 + dg owns output dims dg*8 .. dg*8+7 for the positions p = pg (mod 4); each lane issues
+// one 16-byte load per position (a warp covers 4 positions x 128 B per instruction), the probabilities and cache rows of
+// the 32-position chunk sit in per-warp shared arrays, and the four position groups are summed by two xor-shuffles at
+// the end.  (The previous layout walked the positions one by one with two shuffles and a 4-byte load per lane.)
+struct WarpScratch {
+  float q[DH];        // pre-scaled query
+  float p[32];        // probabilities of the current chunk
+  unsigned row[32];   // K/V rows of the current chunk
+};
+
+template <bool SPLIT>
+__device__ __forceinline__ void pv_accumulate(const Act& vc, int v_col, const WarpScratch& ws, int kmax, int lane, float* o) {
+  const int pg = lane >> 3, dg = lane & 7;
+#pragma unroll 4
+  for (int pp = pg; pp < kmax; pp += 4) {
+    const float w = ws.p[pp];
+    const bf16* src = vc.p + (size_t)ws.row[pp] * vc.ld + v_col + dg * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(src), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(w, f[i], o[i]);
+    if constexpr (SPLIT) {
+      unpack8(*reinterpret_cast<const uint4*>(src + vc.lo), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(w, f[i], o[i]);
+    }
+  }
+}
+
+template <bool SPLIT, typename RowFn>
+__device__ __forceinline__ void warp_attend(WarpScratch& ws, const Act& kc, int k_col, const Act& vc, int v_col, int Tk,
+                                            RowFn krow, int lane, float& m, float& l, float* o) {
   for (int k0 = 0; k0 < Tk; k0 += 32) {
     const int pos = k0 + lane;
     float sc = -INFINITY;
     unsigned myrow = 0;
     if (pos < Tk) {
       myrow = (unsigned)krow(pos);
-      sc = dot_row64(kc, myrow, k_col, qs);
+      sc = dot_row64<SPLIT>(kc, myrow, k_col, ws.q);
     }
     const float mn = fmaxf(m, warp_max(sc));
     const float corr = __expf(m - mn);
     const float p = (pos < Tk) ? __expf(sc - mn) : 0.f;
     l = l * corr + warp_sum(p);
-    o0 *= corr;
-    o1 *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= corr;
     m = mn;
-    const int kmax = min(32, Tk - k0);
-#pragma unroll 8
-    for (int j = 0; j < kmax; ++j) {
-      const unsigned r = __shfl_sync(0xffffffffu, myrow, j);
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      const float2 v = ld_pair(vc, r, v_col, lane);
-      o0 = fmaf(pj, v.x, o0);
-      o1 = fmaf(pj, v.y, o1);
-    }
+    ws.p[lane] = p;
+    ws.row[lane] = myrow;
+    __syncwarp();
+    pv_accumulate<SPLIT>(vc, v_col, ws, min(32, Tk - k0), lane, o);
+    __syncwarp();
+  }
+}
+
+// sum the four position groups; afterwards lanes 0..7 hold dims lane*8 .. lane*8+7
+__device__ __forceinline__ void pv_reduce(float* o) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
   }
 }
 
@@ -183,16 +431,18 @@ constexpr int DEC_WARPS = 4;
 
 // one warp per (row, head).  Position t = *step is the new token: its K/V come from `qkv` and are appended to the
 // cache at [row][t]; positions t' < t are read from cache row anc[row][t'] (the beam's ancestor at that time).
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_self_attention(Act qkv, Act kc, Act vc,
+template <bool SPLIT>
+__global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_attention(Act qkv, Act kc, Act vc,
                                                                        const int* __restrict__ anc_base, size_t anc_stride,
                                                                        const int* __restrict__ step, int rows, int T,
                                                                        int heads, Act out) {
-  __shared__ float sq[DEC_WARPS][DH];
+  __shared__ WarpScratch s_ws[DEC_WARPS];
   pdl_launch();
   pdl_wait();
   const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  WarpScratch& ws = s_ws[w];
   const int row = gw / heads, h = gw % heads;
   const int d = heads * DH;
   const int t = *step;
@@ -200,58 +450,88 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_self_attention(Act qkv, 
   const float2 qv = ld_pair(qkv, row, h * DH, lane);
   const float2 kn = ld_pair(qkv, row, d + h * DH, lane);
   const float2 vn = ld_pair(qkv, row, 2 * d + h * DH, lane);
-  sq[w][lane * 2] = qv.x * 0.125f;       // 1/sqrt(64)
-  sq[w][lane * 2 + 1] = qv.y * 0.125f;
+  ws.q[lane * 2] = qv.x * 0.125f;       // 1/sqrt(64)
+  ws.q[lane * 2 + 1] = qv.y * 0.125f;
   st_pair(kc, (size_t)row * T + t, h * DH, lane, kn.x, kn.y);     // append the new K/V to the cache
   st_pair(vc, (size_t)row * T + t, h * DH, lane, vn.x, vn.y);
   __syncwarp();
-  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  warp_attend(sq[w], kc, h * DH, vc, h * DH, t, [&](int pos) { return (size_t)anc[pos] * T + pos; }, lane, m, l, o0, o1);
-  {   // the new position itself (K/V still in registers)
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  warp_attend<SPLIT>(ws, kc, h * DH, vc, h * DH, t, [&](int pos) { return (size_t)anc[pos] * T + pos; }, lane, m, l, o);
+  pv_reduce(o);
+  {   // the new position itself (K/V still in registers): fold it in on lanes 0..7
     const float sc = warp_sum((qv.x * kn.x + qv.y * kn.y) * 0.125f);
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn);
     const float p = __expf(sc - mn);
     l = l * corr + p;
-    o0 = o0 * corr + p * vn.x;
-    o1 = o1 * corr + p * vn.y;
+    // v_new dims lane*8 .. +7 live on lanes 4*lane .. 4*lane+3 (2 dims each)
+    float vnew[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      vnew[2 * i] = __shfl_sync(0xffffffffu, vn.x, (lane & 7) * 4 + i);
+      vnew[2 * i + 1] = __shfl_sync(0xffffffffu, vn.y, (lane & 7) * 4 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + p * vnew[i];
   }
-  const float inv = 1.f / l;
-  st_pair(out, row, h * DH, lane, o0 * inv, o1 * inv);
+  if (lane < 8) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= inv;
+    st_act8(out, (size_t)row, h * DH + lane * 8, o);
+  }
 }
 int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, const int* step, int rows, int T,
                               int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
-  FPNMT_CUDA_OK(launch_k(k_dec_self_attention, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                         qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
+  if (kcache.lo)
+    FPNMT_CUDA_OK(launch_k(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
+  else
+    FPNMT_CUDA_OK(launch_k(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
   return 0;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows,
+template <bool SPLIT>
+__global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows,
                                                                         int beam, int Tk, int heads, Act out) {
-  __shared__ float sq[DEC_WARPS][DH];
+  __shared__ WarpScratch s_ws[DEC_WARPS];
   pdl_launch();
   pdl_wait();
   const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  WarpScratch& ws = s_ws[w];
   const int row = gw / heads, h = gw % heads;
   const int img = row / beam;
   const float2 qv = ld_pair(q, row, h * DH, lane);
-  sq[w][lane * 2] = qv.x * 0.125f;
-  sq[w][lane * 2 + 1] = qv.y * 0.125f;
+  ws.q[lane * 2] = qv.x * 0.125f;
+  ws.q[lane * 2 + 1] = qv.y * 0.125f;
   __syncwarp();
-  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  warp_attend(sq[w], kv, k_col + h * DH, kv, v_col + h * DH, Tk, [&](int pos) { return (size_t)img * Tk + pos; }, lane,
-              m, l, o0, o1);
-  const float inv = 1.f / l;
-  st_pair(out, row, h * DH, lane, o0 * inv, o1 * inv);
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  warp_attend<SPLIT>(ws, kv, k_col + h * DH, kv, v_col + h * DH, Tk, [&](int pos) { return (size_t)img * Tk + pos; }, lane, m, l, o);
+  pv_reduce(o);
+  if (lane < 8) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= inv;
+    st_act8(out, (size_t)row, h * DH + lane * 8, o);
+  }
 }
 int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam, int Tk, int heads, Act out,
                                cudaStream_t s) {
   const int warps = rows * heads;
-  FPNMT_CUDA_OK(launch_k(k_dec_cross_attention, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                         q, kv, k_col, v_col, rows, beam, Tk, heads, out));
+  if (kv.lo)
+    FPNMT_CUDA_OK(launch_k(k_dec_cross_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           q, kv, k_col, v_col, rows, beam, Tk, heads, out));
+  else
+    FPNMT_CUDA_OK(launch_k(k_dec_cross_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           q, kv, k_col, v_col, rows, beam, Tk, heads, out));
   return 0;
 }
 

@@ -13,7 +13,6 @@ namespace fpnmt {
 
 #define LAUNCH_CHECK() FPNMT_CUDA_OK(cudaGetLastError())
 
-constexpr int RT_MAXV4 = 12;   // float4 loads per thread -> V <= 48 * blockDim
 
 __global__ void k_beam_init(BeamState st, int true_beam) {
   pdl_launch();
@@ -70,8 +69,9 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 //                          handle <end>, write the NEXT step's decoder input rows (embedding + position), and let the
 //                          last image advance the device step counter.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_beam_step(BeamState st, const float* __restrict__ logits, int ld, BeamEmbed em) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(BeamState st, const float* __restrict__ logits, int ld, BeamEmbed em) {
   constexpr int NW = THREADS / 32;
+  extern __shared__ float4 s_row4[];                       // the row's logits (later: candidate scores), nv4*THREADS float4
   __shared__ float s_m[NW], s_s[NW];
   __shared__ float s_cv[NW * 32];
   __shared__ int s_ci[NW * 32];
@@ -85,114 +85,226 @@ __global__ void __launch_bounds__(THREADS) k_beam_step(BeamState st, const float
   const int t = *st.step;
   const float score = st.score[t & 1][row];
   const float* x = logits + (size_t)row * ld;
+  const int nv4 = (V + 4 * THREADS - 1) / (4 * THREADS);  // float4 slots per thread; slot i of thread tid = elements
+  float* s_row = reinterpret_cast<float*>(s_row4);        //   (i*THREADS + tid)*4 .. +3 (conflict-free, coalesced)
 
-  float v[RT_MAXV4 * 4];
-#pragma unroll
-  for (int i = 0; i < RT_MAXV4; ++i) {
-    const int e = (i * THREADS + tid) * 4;
-    if (e + 3 < V) {
-      const float4 q = __ldcs(reinterpret_cast<const float4*>(x + e));
-      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[4 * i + j] = (e + j < V) ? x[e + j] : -INFINITY;
-    }
-  }
-  // ---- row max and sum of exponentials: thread-local (m, s) pairs combined with the online-softmax rule
+  // ---- stage the row in shared memory (registers stay small: every row block of the step is resident at once)
   float m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < RT_MAXV4 * 4; ++i) m = fmaxf(m, v[i]);
+#pragma unroll 4
+  for (int i = 0; i < nv4; ++i) {
+    const int e = (i * THREADS + tid) * 4;
+    float4 q;
+    if (e + 3 < V) {
+      q = __ldcs(reinterpret_cast<const float4*>(x + e));
+    } else {
+      q.x = (e < V) ? x[e] : -INFINITY;
+      q.y = (e + 1 < V) ? x[e + 1] : -INFINITY;
+      q.z = (e + 2 < V) ? x[e + 2] : -INFINITY;
+      q.w = (e + 3 < V) ? x[e + 3] : -INFINITY;
+    }
+    s_row4[i * THREADS + tid] = q;
+    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+  const float tmax_v = m;                                  // this thread's largest logit
+  // ---- row max and sum of exponentials
   m = warp_max(m);
   if (lane == 0) s_m[warp] = m;
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < NW; ++w) m = fmaxf(m, s_m[w]);
   float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < RT_MAXV4 * 4; ++i) sum += expf(v[i] - m);   // exp(-inf) = 0 for the padding
+#pragma unroll 4
+  for (int i = 0; i < nv4; ++i) {
+    const float4 q = s_row4[i * THREADS + tid];
+    sum += expf(q.x - m) + expf(q.y - m) + expf(q.z - m) + expf(q.w - m);   // exp(-inf) = 0 for the padding
+  }
   sum = warp_sum(sum);
   if (lane == 0) s_s[warp] = sum;
   __syncthreads();
   sum = 0.f;
 #pragma unroll
   for (int w = 0; w < NW; ++w) sum += s_s[w];
-  // ---- candidate scores (pipeline.py:117,122 in prob mode; the same ordering in the log domain otherwise)
-  if (st.prob_mode) {
-#pragma unroll
-    for (int i = 0; i < RT_MAXV4 * 4; ++i) v[i] = (expf(v[i] - m) / sum) * score;
-  } else {
-    const float lse = m + logf(sum);
-#pragma unroll
-    for (int i = 0; i < RT_MAXV4 * 4; ++i) v[i] = score + (v[i] - lse);
-  }
-#pragma unroll
-  for (int i = 0; i < RT_MAXV4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((i * THREADS + tid) * 4 + j >= V) v[4 * i + j] = -INFINITY;
-  // ---- per-warp top-N: the lane that owns the round's winner is the only one that rescans
-  unsigned long long taken = 0ull;
-  float bv;
-  int bi;
-  auto rescan = [&]() {
-    bv = -INFINITY;
-    bi = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < RT_MAXV4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = (i * THREADS + tid) * 4 + j;
-        const bool free_slot = !((taken >> (4 * i + j)) & 1ull) && e < V;
-        if (free_slot && better(v[4 * i + j], e, bv, bi)) {
-          bv = v[4 * i + j];
-          bi = e;
-        }
-      }
-  };
-  rescan();
-  for (int k = 0; k < N; ++k) {
-    float wv = bv;
-    int wi = bi;
-    warp_argmax(wv, wi);
-    if (lane == 0) {
-      s_cv[warp * 32 + k] = wv;
-      s_ci[warp * 32 + k] = wi;
-    }
-    if (wi == bi && bi != 0x7fffffff) {                    // element indices are unique -> exactly one owner
-      const int slot4 = bi >> 2;
-      taken |= 1ull << (4 * (slot4 / THREADS) + (bi & 3));
-      rescan();
+  // ---- candidate score of a logit (pipeline.py:117,122 in prob mode; the same ordering in the log domain otherwise).
+  // Every step of it is monotone non-decreasing in floating point, so max_e cand(v_e) == cand(max_e v_e) exactly.
+  const float lse = m + logf(sum);
+  const bool prob = st.prob_mode != 0;
+  auto cand = [&](float vv) -> float { return prob ? (expf(vv - m) / sum) * score : score + (vv - lse); };
+
+  // ---- row-local top-N (tf.math.top_k order: value descending, lower index first).
+  // Fast path: tau = N-th largest of the per-thread maxima is a lower bound of the N-th largest candidate, so every
+  // winner satisfies c >= tau; those few elements (typically N..2N of V) are gathered into a shared list and warp 0
+  // selects among them.  If more than CAP elements reach tau (massive ties, e.g. the reference's probability
+  // underflow regime where every candidate is 0), the exact but slower rescan path below takes over.
+  constexpr int CAP = 128;
+  __shared__ float s_lv[CAP];
+  __shared__ int s_li[CAP];
+  __shared__ float s_tau;
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  {
+    float tm = cand(tmax_v);
+    for (int k = 0; k < N; ++k) {                           // per warp: its N largest thread maxima (values only)
+      const float w = warp_max(tm);
+      if (lane == 0) s_cv[warp * 32 + k] = w;
+      const unsigned hit = __ballot_sync(0xffffffffu, tm == w);
+      if (lane == __ffs(hit) - 1) tm = -INFINITY;
     }
   }
   __syncthreads();
-  // ---- warp 0 merges the NW*N survivors (lane k holds the k-th candidate of every warp; N <= 32)
   if (warp == 0) {
     float cv[NW];
-    int ci[NW];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const bool ok = lane < N;
-      cv[w] = ok ? s_cv[w * 32 + lane] : -INFINITY;
-      ci[w] = ok ? s_ci[w * 32 + lane] : 0x7fffffff;
-    }
+    for (int w = 0; w < NW; ++w) cv[w] = lane < N ? s_cv[w * 32 + lane] : -INFINITY;
+    float tau = -INFINITY;
     for (int k = 0; k < N; ++k) {
       float b2 = -INFINITY;
-      int i2 = 0x7fffffff;
 #pragma unroll
-      for (int w = 0; w < NW; ++w)
-        if (ci[w] != 0x7fffffff && better(cv[w], ci[w], b2, i2)) {
-          b2 = cv[w];
-          i2 = ci[w];
-        }
-      warp_argmax(b2, i2);
+      for (int w = 0; w < NW; ++w) b2 = fmaxf(b2, cv[w]);
+      tau = warp_max(b2);
+      const unsigned hit = __ballot_sync(0xffffffffu, b2 == tau);
+      if (lane == __ffs(hit) - 1) {                         // drop ONE instance of the maximum
+        bool dropped = false;
 #pragma unroll
-      for (int w = 0; w < NW; ++w)
-        if (ci[w] == i2) ci[w] = 0x7fffffff;
-      if (lane == 0) {
-        st.cand_val[(size_t)row * N + k] = b2;
-        st.cand_idx[(size_t)row * N + k] = i2;
+        for (int w = 0; w < NW; ++w)
+          if (!dropped && cv[w] == tau) {
+            cv[w] = -INFINITY;
+            dropped = true;
+          }
       }
     }
+    if (lane == 0) s_tau = tau;
+  }
+  __syncthreads();
+  {
+    const float tau = s_tau;
+#pragma unroll 2
+    for (int i = 0; i < nv4; ++i) {
+      const float4 q = s_row4[i * THREADS + tid];
+      const float c4[4] = {cand(q.x), cand(q.y), cand(q.z), cand(q.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i * THREADS + tid) * 4 + j;
+        if (e < V && c4[j] >= tau) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < CAP) {
+            s_lv[pos] = c4[j];
+            s_li[pos] = e;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (cnt <= CAP && cnt >= N) {
+    if (warp == 0) {
+      float cv[CAP / 32];
+      int ci[CAP / 32];
+#pragma unroll
+      for (int q = 0; q < CAP / 32; ++q) {
+        const int idx = lane + 32 * q;
+        cv[q] = idx < cnt ? s_lv[idx] : -INFINITY;
+        ci[q] = idx < cnt ? s_li[idx] : 0x7fffffff;
+      }
+      for (int k = 0; k < N; ++k) {
+        float b2 = -INFINITY;
+        int i2 = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < CAP / 32; ++q)
+          if (ci[q] != 0x7fffffff && better(cv[q], ci[q], b2, i2)) {
+            b2 = cv[q];
+            i2 = ci[q];
+          }
+        warp_argmax(b2, i2);
+#pragma unroll
+        for (int q = 0; q < CAP / 32; ++q)
+          if (ci[q] == i2) ci[q] = 0x7fffffff;
+        if (lane == 0) {
+          st.cand_val[(size_t)row * N + k] = b2;
+          st.cand_idx[(size_t)row * N + k] = i2;
+        }
+      }
+    }
+  } else {
+    // ---- exact fallback: candidate scores written back to shared memory; per-warp top-N by shuffle arg-max rounds
+    // in which the owning lane knocks its winner out (-inf) and rescans its slots; then warp 0 merges the survivors.
+    for (int i = 0; i < nv4; ++i) {
+      float4 q = s_row4[i * THREADS + tid];
+      const int e = (i * THREADS + tid) * 4;
+      q.x = (e < V) ? cand(q.x) : -INFINITY;
+      q.y = (e + 1 < V) ? cand(q.y) : -INFINITY;
+      q.z = (e + 2 < V) ? cand(q.z) : -INFINITY;
+      q.w = (e + 3 < V) ? cand(q.w) : -INFINITY;
+      s_row4[i * THREADS + tid] = q;
+    }
+    unsigned long long taken_lo = 0ull;                     // knocked-out slots of this thread (up to 64 elements;
+    unsigned long long taken_hi = 0ull;                     //  second word for rows longer than 16 float4 per thread)
+    float bv;
+    int bi;
+    auto is_taken = [&](int s) { return s < 64 ? ((taken_lo >> s) & 1ull) != 0 : ((taken_hi >> (s - 64)) & 1ull) != 0; };
+    auto rescan = [&]() {
+      bv = -INFINITY;
+      bi = 0x7fffffff;
+      for (int i = 0; i < nv4; ++i) {
+        const float4 q = s_row4[i * THREADS + tid];
+        const float c4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = (i * THREADS + tid) * 4 + j;
+          if (e < V && !is_taken(4 * i + j) && better(c4[j], e, bv, bi)) {
+            bv = c4[j];
+            bi = e;
+          }
+        }
+      }
+    };
+    rescan();
+    for (int k = 0; k < N; ++k) {
+      float wv = bv;
+      int wi = bi;
+      warp_argmax(wv, wi);
+      if (lane == 0) {
+        s_cv[warp * 32 + k] = wv;
+        s_ci[warp * 32 + k] = wi;
+      }
+      if (wi == bi && bi != 0x7fffffff) {                  // element indices are unique -> exactly one owner
+        const int slot = 4 * ((bi >> 2) / THREADS) + (bi & 3);
+        if (slot < 64) taken_lo |= 1ull << slot;
+        else taken_hi |= 1ull << (slot - 64);
+        rescan();
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float cv[NW];
+      int ci[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const bool ok = lane < N;
+        cv[w] = ok ? s_cv[w * 32 + lane] : -INFINITY;
+        ci[w] = ok ? s_ci[w * 32 + lane] : 0x7fffffff;
+      }
+      for (int k = 0; k < N; ++k) {
+        float b2 = -INFINITY;
+        int i2 = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+          if (ci[w] != 0x7fffffff && better(cv[w], ci[w], b2, i2)) {
+            b2 = cv[w];
+            i2 = ci[w];
+          }
+        warp_argmax(b2, i2);
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+          if (ci[w] == i2) ci[w] = 0x7fffffff;
+        if (lane == 0) {
+          st.cand_val[(size_t)row * N + k] = b2;
+          st.cand_idx[(size_t)row * N + k] = i2;
+        }
+      }
+    }
+  }
+  if (warp == 0) {
     __syncwarp();
     if (lane == 0) {
       __threadfence();                                      // candidates visible before the image counter moves
@@ -315,18 +427,27 @@ __global__ void __launch_bounds__(THREADS) k_beam_step(BeamState st, const float
   }
 }
 int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s) {
-  if (512 * RT_MAXV4 * 4 < st.V) {
-    set_last_error("beam_step: vocabulary too large (max 24576)");
-    return 1;
-  }
   if (st.N > 32 || (ld & 3)) {
     set_last_error("beam_step: beam width must be <= 32 and logits ld a multiple of 4");
     return 1;
   }
-  if (256 * RT_MAXV4 * 4 >= st.V)
-    FPNMT_CUDA_OK(launch_k(k_beam_step<256>, dim3(st.B * st.N), dim3(256), 0, s, st, logits, ld, em));
+  const int threads = st.V <= 16384 ? 256 : 512;
+  const int nv4 = (st.V + 4 * threads - 1) / (4 * threads);
+  const size_t smem = (size_t)nv4 * threads * 16;
+  if (nv4 > 32 || smem > 200 * 1024) {
+    set_last_error("beam_step: vocabulary too large (max 65536)");
+    return 1;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  if (threads == 256)
+    FPNMT_CUDA_OK(launch_k(k_beam_step<256>, dim3(st.B * st.N), dim3(256), smem, s, st, logits, ld, em));
   else
-    FPNMT_CUDA_OK(launch_k(k_beam_step<512>, dim3(st.B * st.N), dim3(512), 0, s, st, logits, ld, em));
+    FPNMT_CUDA_OK(launch_k(k_beam_step<512>, dim3(st.B * st.N), dim3(512), smem, s, st, logits, ld, em));
   return 0;
 }
 

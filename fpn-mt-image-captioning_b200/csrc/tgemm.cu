@@ -178,11 +178,21 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           tc_fence_after();
           if (g == 0 && rt == rt0) DBG(3);
           const int n = min(G, kiters - g * G);
-          for (int i = 0; i < n; ++i) {
-            const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (sa * G + i) * TG_A_BYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (sb * G + i) * B_BYTES));
+          const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA + sa * G * TG_A_BYTES));
+          const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB + sb * G * B_BYTES));
+          if (n == G) {                            // full group: 16 back-to-back MMAs, descriptors advance by constants
 #pragma unroll
-            for (int k = 0; k < TG_BK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
+            for (int i = 0; i < G; ++i)
+#pragma unroll
+              for (int k = 0; k < TG_BK / 16; ++k)
+                umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
+                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
+          } else {
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+              for (int k = 0; k < TG_BK / 16; ++k)
+                umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
+                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&emptyB[sb]);
           if (!p.stationary) umma_commit(&emptyA[sa]);

@@ -210,3 +210,24 @@ def test_engine_matches_reference_goldens():
         for i in range(2):
             assert ids[i, :lens[i]].tolist() == gold["predict_beam%d_img%d" % (beam, i)].tolist(), (beam, i)
         eng.close()
+
+
+def test_encoder_attention_mma_matches_simt_path():
+    """bf16 mode: the mma.sync flash kernel of the encoder's cross-level attention vs the fp32 CUDA-core kernel on the
+    same bf16 K/V/Q (the only differences are P rounded to bf16 and the summation order): encoder layers within 2e-2."""
+    import os
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=7)
+    img = O.test_images(B, 512, seed=4)           # 512x512: the P3 view has 1024 keys (16 tiles of 64)
+    outs = {}
+    for mode in ("0", "1"):
+        os.environ["FPNMT_ENC_ATT_SIMT"] = mode
+        eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16",
+                     use_graphs=False)
+        eng.encode(img.cuda())
+        outs[mode] = [eng.tap("enc_layer%d" % l).cpu() for l in range(L)]
+        eng.close()
+    os.environ.pop("FPNMT_ENC_ATT_SIMT", None)
+    for l in range(L):
+        assert rel(outs["0"][l], outs["1"][l]) < 2e-2, (l, rel(outs["0"][l], outs["1"][l]))

@@ -45,6 +45,17 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, int distinct_a, long 
     out[0] = t1 - t0;
     out[1] = t2 - t0;
     out[2] = g1 - g0;
+  } else if ((distinct_a & 8) && warp == 2 && lane == 0) {
+    // second issuer on another scheduler, own accumulator columns, own completion barrier
+    for (int it = 0; it < n_mma / 4; ++it) {
+      const uint64_t ad = umma_desc_sw128(smem_u32(smem + ((it + 2) % 4) * 16384));
+      const uint64_t bd = umma_desc_sw128(smem_u32(smem + 4 * 16384 + ((it + 2) % 4) * BN * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tm + 256, ad + 2 * k, bd + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+    }
+    umma_commit(&side[0]);
+    mbar_wait(&side[0], 0);
+    out[3] = clock64();
   } else if ((distinct_a & 4) && warp >= 2) {
     mbar_wait(&bar, 0);
   }
@@ -66,7 +77,7 @@ void run(int n, int da) {
 }
 
 int main() {
-  for (int da = 0; da < 8; ++da) {
+  for (int da = 0; da < 16; da += 8) {
     run<32>(32, da); run<32>(256, da);
     run<64>(32, da); run<64>(256, da);
     run<128>(32, da); run<128>(256, da);
