@@ -267,16 +267,30 @@ def run_own(args, wl):
     enc_us = sum(o["us"] for o in enc_ops)
     step_us = sum(o["us"] for o in step_ops)
     tail = [o for o in step_ops if o["kind"] == "beam"]
+    step_by_kind = {}
+    for o in step_ops:
+        step_by_kind[o["kind"]] = step_by_kind.get(o["kind"], 0.0) + o["us"]
     tail_us, tail_bytes = sum(o["us"] for o in tail), sum(o["bytes"] for o in tail)
     achieved = top["flops"] / (top["us"] * 1e-6) / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_igemm_encode.json")
+    if wl["backbone"] == "resnet50" and os.path.exists(tpath):      # ncu --set full capture of the same kernel, C2
+        with open(tpath) as f:
+            tt = json.load(f)
+        if top["name"] in tt["ops"]:
+            traffic = tt["ops"][top["name"]]["dram_bytes"]
+            traffic_src = "profiles/r01_ncu_traffic_igemm_encode.json (ncu, one launch, cold cache)"
     roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM) @ " + top["name"], "achieved": achieved,
-                "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"], "traffic": None,
+                "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"], "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_flops_per_launch": top["flops"],
+                "algorithmic_bytes_per_launch": top["bytes"], "launch_us": top["us"],
                 "peak_source": peaks["source"] + ", burst bf16 cuBLAS",
                 "all_igemm": {"achieved": ig_flops / (ig_us * 1e-6) / 1e12, "share_of_encode": ig_us / enc_us,
                               "launches": len(ig)},
                 "decode_tail": {"bound": "hbm", "achieved_gbs": tail_bytes / (tail_us * 1e-6) / 1e9 if tail_us else None,
                                 "peak_gbs": peaks["hbm_gbs"], "us": tail_us},
-                "encode_us_sum": enc_us, "decode_step_us_sum": step_us}
+                "encode_us_sum": enc_us, "decode_step_us_sum": step_us, "decode_step_us_by_kind": step_by_kind,
+                "decode_step_kernels": len(step_ops)}
     cb = None
     if world == 1 and not args.no_cpu:
         cb = cpu_reference_sample(wl, 3, 1)

@@ -252,134 +252,195 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       tc_fence_after();
       if (e == 0 && lane == 0) DBG(5);
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      // Units are processed in PAIRS so that two independent instruction streams (TMEM load, staging round trip,
+      // stores) overlap inside each latency-bound epilogue warp; the activation switch is hoisted out of the loops.
 #pragma unroll 1
-      for (int j = 0; j < nu; ++j) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + (u0 + j) * 32, r);
+      for (int j = 0; j < nu; j += 2) {
+        const bool two = (j + 1 < nu);
+        uint32_t r[2][32];
+        tmem_ld32(t_addr + (u0 + j) * 32, r[0]);
+        if (two) tmem_ld32(t_addr + (u0 + j + 1) * 32, r[1]);
         tmem_ld_wait();
-        const int col0 = co_t * BN + (u0 + j) * 32;
-        if (col0 >= p.Cout) continue;        // warp-uniform
-        uint8_t* buf = my_stage + j * UNIT_BYTES;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int colA = co_t * BN + (u0 + j) * 32;
+        if (colA >= p.Cout) continue;        // warp-uniform (both units are beyond Cout)
+        const int nun = (two && colA + 32 < p.Cout) ? 2 : 1;
         if (fast) {
+          float v[2][32];
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[q][i] = __uint_as_float(r[q][i]);
           // ---- bias (bias arrays are padded to a multiple of 32 floats)
           if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + i * 4);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int q = 0; q < 2; ++q) {
+              if (q < nun) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + colA + q * 32 + i * 4));
+                  v[q][4 * i] += b.x; v[q][4 * i + 1] += b.y; v[q][4 * i + 2] += b.z; v[q][4 * i + 3] += b.w;
+                }
+              }
             }
           }
           // ---- residual
           if (p.res_mode != RES_NONE) {
-            cp_async_wait_pending(nu - 1 - j);
+            cp_async_wait_pending(nu - j - nun);
             __syncwarp();
             if (e == 0 && lane == 0) DBG(6);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float f[8];
-              unpack8(*stage_ptr(buf, lane, c), f);
+            for (int q = 0; q < 2; ++q) {
+              if (q < nun) {
+                uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
+                for (int c = 0; c < 4; ++c) {
+                  float f[8];
+                  unpack8(*stage_ptr(buf, lane, c), f);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[q][c * 8 + i] += f[i];
+                }
+              }
             }
             __syncwarp();
             if (p.res.lo) {                  // split residual: low halves, synchronous transposed load
+              for (int q = 0; q < nun; ++q) {
+                uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = i * 8 + t_r;
-                const long long off = my_off[32 + rr];
-                const int col = col0 + t_c * 8;
-                const bool ok = off >= 0 && col < p.Cout;
-                const bf16* src = p.res.p + p.res.lo + (ok ? (size_t)off * p.res.ld + col : 0);
-                cp_async16(stage_ptr(buf, rr, t_c), src, ok);
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = i * 8 + t_r;
+                  const long long off = my_off[32 + rr];
+                  const int col = colA + q * 32 + t_c * 8;
+                  const bool ok = off >= 0 && col < p.Cout;
+                  const bf16* src = p.res.p + p.res.lo + (ok ? (size_t)off * p.res.ld + col : 0);
+                  cp_async16(stage_ptr(buf, rr, t_c), src, ok);
+                }
               }
               cp_async_commit();
               cp_async_wait_pending(0);
               __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float f[8];
-                unpack8(*stage_ptr(buf, lane, c), f);
+              for (int q = 0; q < 2; ++q) {
+                if (q < nun) {
+                  uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
+                  for (int c = 0; c < 4; ++c) {
+                    float f[8];
+                    unpack8(*stage_ptr(buf, lane, c), f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[q][c * 8 + i] += f[i];
+                  }
+                }
               }
               __syncwarp();
             }
           }
+          // ---- activation (switch hoisted: one predictable branch per pair instead of three compares per element)
+          if (p.act == ACT_RELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-          // ---- bf16 output through the staging buffer, transposed 16-byte stores
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
+          } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[q][i] = v[q][i] >= 0.f ? v[q][i] : 0.2f * v[q][i];
+          } else if (p.act == ACT_RELU6) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[q][i] = fminf(fmaxf(v[q][i], 0.f), 6.f);
+          }
+          // ---- bf16 output through the staging buffers, transposed 16-byte stores
           if (p.out.p) {
-            uint4 hi[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              hi[c] = pack8(v + c * 8);
-              *stage_ptr(buf, lane, c) = hi[c];
+            for (int q = 0; q < 2; ++q) {
+              if (q < nun) {
+                uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *stage_ptr(buf, lane, c) = pack8(v[q] + c * 8);
+              }
             }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = i * 8 + t_r;
               const long long off = my_off[rr];
-              const int col = col0 + t_c * 8;
-              if (off >= 0 && col < p.Cout)
-                *reinterpret_cast<uint4*>(p.out.p + (size_t)off * p.out.ld + col) = *stage_ptr(buf, rr, t_c);
+              bf16* dst = p.out.p + (size_t)(off < 0 ? 0 : off) * p.out.ld + colA + t_c * 8;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                if (q < nun && off >= 0 && colA + q * 32 + t_c * 8 < p.Cout)
+                  *reinterpret_cast<uint4*>(dst + q * 32) = *stage_ptr(my_stage + (j + q) * UNIT_BYTES, rr, t_c);
+              }
             }
             __syncwarp();
             if (p.out.lo) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float hf[8], lo[8];
-                unpack8(hi[c], hf);
+              for (int q = 0; q < 2; ++q) {
+                if (q < nun) {
+                  uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) lo[i] = v[c * 8 + i] - hf[i];
-                *stage_ptr(buf, lane, c) = pack8(lo);
+                  for (int c = 0; c < 4; ++c) {
+                    float hf[8], lo[8];
+                    unpack8(pack8(v[q] + c * 8), hf);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) lo[i] = v[q][c * 8 + i] - hf[i];
+                    *stage_ptr(buf, lane, c) = pack8(lo);
+                  }
+                }
               }
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rr = i * 8 + t_r;
                 const long long off = my_off[rr];
-                const int col = col0 + t_c * 8;
-                if (off >= 0 && col < p.Cout)
-                  *reinterpret_cast<uint4*>(p.out.p + p.out.lo + (size_t)off * p.out.ld + col) = *stage_ptr(buf, rr, t_c);
+                bf16* dst = p.out.p + p.out.lo + (size_t)(off < 0 ? 0 : off) * p.out.ld + colA + t_c * 8;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  if (q < nun && off >= 0 && colA + q * 32 + t_c * 8 < p.Cout)
+                    *reinterpret_cast<uint4*>(dst + q * 32) = *stage_ptr(my_stage + (j + q) * UNIT_BYTES, rr, t_c);
+                }
               }
               __syncwarp();
             }
           }
           // ---- fp32 output: two 16-column halves (64 B per row each) through the same buffer
           if (p.out_f32) {
+            for (int q = 0; q < nun; ++q) {
+              uint8_t* buf = my_stage + (j + q) * UNIT_BYTES;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+              for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *stage_ptr(buf, lane, c) = make_uint4(__float_as_uint(v[hh * 16 + c * 4]), __float_as_uint(v[hh * 16 + c * 4 + 1]),
-                                                      __float_as_uint(v[hh * 16 + c * 4 + 2]), __float_as_uint(v[hh * 16 + c * 4 + 3]));
-              __syncwarp();
+                for (int c = 0; c < 4; ++c)
+                  *stage_ptr(buf, lane, c) = make_uint4(__float_as_uint(v[q][hh * 16 + c * 4]), __float_as_uint(v[q][hh * 16 + c * 4 + 1]),
+                                                        __float_as_uint(v[q][hh * 16 + c * 4 + 2]), __float_as_uint(v[q][hh * 16 + c * 4 + 3]));
+                __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = i * 8 + t_r;
-                const long long off = my_off[rr];
-                const int col = col0 + hh * 16 + t_c * 4;
-                if (off >= 0 && col < p.Cout)
-                  *reinterpret_cast<uint4*>(p.out_f32 + (size_t)off * p.ld_f32 + col) = *stage_ptr(buf, rr, t_c);
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = i * 8 + t_r;
+                  const long long off = my_off[rr];
+                  const int col = colA + q * 32 + hh * 16 + t_c * 4;
+                  if (off >= 0 && col < p.Cout)
+                    *reinterpret_cast<uint4*>(p.out_f32 + (size_t)off * p.ld_f32 + col) = *stage_ptr(buf, rr, t_c);
+                }
+                __syncwarp();
               }
-              __syncwarp();
             }
           }
         } else if (valid) {
           // ---- generic scalar path (Cout not a multiple of 8, e.g. the 1-channel score map)
+          for (int q = 0; q < nun; ++q) {
+            const int col0 = colA + q * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (col0 + i >= p.Cout) break;
-            float t = v[i];
-            if (p.bias) t += p.bias[col0 + i];
-            if (p.res_mode != RES_NONE) t += ld_act(p.res, rpix, col0 + i);
-            t = apply_act(t, p.act);
-            if (p.out.p) st_act(p.out, pix, col0 + i, t);
-            if (p.out_f32) p.out_f32[pix * (size_t)p.ld_f32 + col0 + i] = t;
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i >= p.Cout) break;
+              float t = __uint_as_float(r[q][i]);
+              if (p.bias) t += p.bias[col0 + i];
+              if (p.res_mode != RES_NONE) t += ld_act(p.res, rpix, col0 + i);
+              t = apply_act(t, p.act);
+              if (p.out.p) st_act(p.out, pix, col0 + i, t);
+              if (p.out_f32) p.out_f32[pix * (size_t)p.ld_f32 + col0 + i] = t;
+            }
           }
         }
       }
