@@ -217,6 +217,11 @@ def run_own(args, wl):
     for i in range(max(args.warmup, 3)):
         step_device(i)
     torch.cuda.synchronize()
+    if args.ncu_step:        # `ncu --profile-from-start off ... bench.py --ncu-step`: capture exactly ONE whole step
+        torch.cuda.cudart().cudaProfilerStart()
+        step_device(0)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     # ---- device-resident timing
     sampler = ClockSampler(local)
     if rank == 0:
@@ -261,36 +266,72 @@ def run_own(args, wl):
         with open(args.profile_out, "w") as f:
             json.dump(prof, f, indent=1)
     enc_ops, step_ops = prof["encode"], prof["decode_step"]
-    ig = [o for o in enc_ops if o["kind"] == "igemm"]
-    top = max(ig, key=lambda o: o["us"])
-    ig_us, ig_flops = sum(o["us"] for o in ig), sum(o["flops"] for o in ig)
-    enc_us = sum(o["us"] for o in enc_ops)
-    step_us = sum(o["us"] for o in step_ops)
-    tail = [o for o in step_ops if o["kind"] == "beam"]
-    step_by_kind = {}
-    for o in step_ops:
-        step_by_kind[o["kind"]] = step_by_kind.get(o["kind"], 0.0) + o["us"]
-    tail_us, tail_bytes = sum(o["us"] for o in tail), sum(o["bytes"] for o in tail)
-    achieved = top["flops"] / (top["us"] * 1e-6) / 1e12
+    T_steps = T
+    # ---- per kernel family: launches per step, device time per step, algorithmic FLOPs / bytes per step
+    fam = {}
+
+    def add(ops, mult, family_of):
+        for o in ops:
+            f = fam.setdefault(family_of(o), dict(launches=0, us=0.0, flops=0.0, bytes=0.0))
+            f["launches"] += mult
+            f["us"] += o["us"] * mult
+            f["flops"] += o["flops"] * mult
+            f["bytes"] += o["bytes"] * mult
+    names = {"igemm": "igemm_kernel (tcgen05 implicit-GEMM convolutions / encoder projections)",
+             "tgemm": "tgemm_kernel (tcgen05 skinny-row Dense layers of the decode step, LayerNorm fused)",
+             "attention": "attention kernels (mma.sync encoder flash attention; decode self/cross attention)",
+             "beam": "k_beam_step (softmax statistics + top-k over beam x vocab + beam bookkeeping)",
+             "elementwise": "elementwise NHWC kernels (im2col, pooling, co-attention, LayerNorm, ...)"}
+    add(enc_ops, 1, lambda o: o["kind"])
+    add(prof.get("decode_init", []), 1, lambda o: o["kind"])
+    add(step_ops, T_steps, lambda o: o["kind"])
+    total_us = sum(f["us"] for f in fam.values())
+    dom = max(fam, key=lambda k: fam[k]["us"])
+    traffic_tables = {}
+    for fn in ("r01_ncu_traffic_igemm_encode.json", "r01_ncu_traffic_decode_step.json"):
+        pth = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(pth):
+            with open(pth) as f:
+                traffic_tables[fn] = json.load(f)
+
+    def family_entry(k):
+        f = fam[k]
+        per_launch_us = f["us"] / f["launches"]
+        tensor = k in ("igemm", "tgemm")
+        # a kernel timed inside a long step: sustained bf16 peak; HBM peak for the bandwidth-bound families
+        peak = peaks["tf_sustained"] if tensor else peaks["hbm_gbs"]
+        ach = (f["flops"] / (f["us"] * 1e-6) / 1e12) if tensor else (f["bytes"] / (f["us"] * 1e-6) / 1e9)
+        return {"kernel": names.get(k, k), "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "launches_per_step": f["launches"],
+                "avg_launch_us": per_launch_us, "share_of_step_device_time": f["us"] / total_us,
+                "algorithmic_per_launch": (f["flops"] if tensor else f["bytes"]) / f["launches"]}
+    roofline = family_entry(dom)
+    # measured DRAM traffic per launch of the dominant family (ncu --set full captures summarised under profiles/)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_igemm_encode.json")
-    if wl["backbone"] == "resnet50" and os.path.exists(tpath):      # ncu --set full capture of the same kernel, C2
-        with open(tpath) as f:
-            tt = json.load(f)
-        if top["name"] in tt["ops"]:
-            traffic = tt["ops"][top["name"]]["dram_bytes"]
-            traffic_src = "profiles/r01_ncu_traffic_igemm_encode.json (ncu, one launch, cold cache)"
-    roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM) @ " + top["name"], "achieved": achieved,
-                "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"], "traffic": traffic,
-                "traffic_source": traffic_src, "algorithmic_flops_per_launch": top["flops"],
-                "algorithmic_bytes_per_launch": top["bytes"], "launch_us": top["us"],
-                "peak_source": peaks["source"] + ", burst bf16 cuBLAS",
-                "all_igemm": {"achieved": ig_flops / (ig_us * 1e-6) / 1e12, "share_of_encode": ig_us / enc_us,
-                              "launches": len(ig)},
-                "decode_tail": {"bound": "hbm", "achieved_gbs": tail_bytes / (tail_us * 1e-6) / 1e9 if tail_us else None,
-                                "peak_gbs": peaks["hbm_gbs"], "us": tail_us},
-                "encode_us_sum": enc_us, "decode_step_us_sum": step_us, "decode_step_us_by_kind": step_by_kind,
-                "decode_step_kernels": len(step_ops)}
+    if dom == "tgemm" and "r01_ncu_traffic_decode_step.json" in traffic_tables:
+        ks = traffic_tables["r01_ncu_traffic_decode_step.json"]["kernels"]
+        tg = [v for k, v in ks.items() if k.startswith("tgemm_kernel")]
+        if tg:
+            traffic = sum(v["mean_dram_bytes"] * v["launches"] for v in tg) / sum(v["launches"] for v in tg)
+            traffic_src = "profiles/r01_ncu_traffic_decode_step.json (ncu --set full, mean over 11 tgemm launches, cold cache)"
+    elif dom == "igemm" and "r01_ncu_traffic_igemm_encode.json" in traffic_tables and wl["backbone"] == "resnet50":
+        ops_t = traffic_tables["r01_ncu_traffic_igemm_encode.json"]["ops"]
+        traffic = sum(v["dram_bytes"] for v in ops_t.values()) / len(ops_t)
+        traffic_src = "profiles/r01_ncu_traffic_igemm_encode.json (ncu, mean over the 124 igemm launches of one encode)"
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = traffic_src
+    roofline["peak_source"] = peaks["source"] + (", sustained bf16 cuBLAS (kernel timed inside a long step)" if roofline["bound"] == "tensor"
+                                                 else ", STREAM-style copy")
+    roofline["note"] = ("dominant = kernel family with the largest share of the step's device time; live per-op CUDA-event "
+                        "timing by fpnmt_profile right after the timed region")
+    roofline["families"] = {k: family_entry(k) for k in fam}
+    ig = [o for o in enc_ops if o["kind"] == "igemm"]
+    best = max(ig, key=lambda o: o["flops"] / o["us"])
+    roofline["best_tensor_launch"] = {"op": best["name"], "achieved": best["flops"] / (best["us"] * 1e-6) / 1e12, "unit": "TFLOP/s",
+                                      "frac_of_burst_peak": best["flops"] / (best["us"] * 1e-6) / 1e12 / peaks["tf"], "us": best["us"]}
+    roofline["encode_us_sum"] = sum(o["us"] for o in enc_ops)
+    roofline["decode_step_us_sum"] = sum(o["us"] for o in step_ops)
+    roofline["decode_step_kernels"] = len(step_ops)
     cb = None
     if world == 1 and not args.no_cpu:
         cb = cpu_reference_sample(wl, 3, 1)
@@ -324,6 +365,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-iters", type=int, default=10)
     ap.add_argument("--profile-out", default=None, help="write the engine's per-op profile (JSON) here")
+    ap.add_argument("--ncu-step", action="store_true", help="bracket one warm step with cudaProfilerStart/Stop (for ncu launch lists)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

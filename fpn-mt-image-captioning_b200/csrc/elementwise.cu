@@ -39,47 +39,49 @@ __global__ void k_im2col_stem(const float* const* __restrict__ img_slot, int N, 
   }
   st_act8(out, pix, g * 8, v);
 }
-// Tiled stride-2 variant: a block stages the KH input rows x (2*63 + KW) columns feeding 64 consecutive output pixels of
-// one output row in shared memory with coalesced loads (each image element leaves L2 once per block instead of once per
-// tap), then writes the 64 im2col rows — one contiguous span of 64 * Kpad bf16 — with 16-byte stores.
+// Tiled stride-2 variant: a block stages the input rows/columns feeding a 64 x 4 tile of output pixels in shared memory
+// with coalesced loads (each image element leaves L2 about once instead of once per tap), then writes the im2col rows
+// (64 * Kpad contiguous bf16 per output row) with 16-byte stores.
 template <int KH, int KW, int PAD>
 __global__ void __launch_bounds__(256) k_im2col_stem_s2(const float* const* __restrict__ img_slot, int N, int H, int W, int Ho,
                                                         int Wo, Act out) {
-  constexpr int TW = 64;
+  constexpr int TW = 64, TH = 4;
+  constexpr int ROWS = (TH - 1) * 2 + KH;
   constexpr int ROWF = ((TW - 1) * 2 + KW) * 3;
   constexpr int KTOT = KH * KW * 3;
-  __shared__ float s[KH][ROWF];
+  __shared__ float s[ROWS][ROWF];
   pdl_launch();
   pdl_wait();
   const float* __restrict__ img = *img_slot;
-  const int xo0 = blockIdx.x * TW, yo = blockIdx.y, n = blockIdx.z;
-  const int x_in0 = xo0 * 2 - PAD, y_in0 = yo * 2 - PAD;
-  for (int i = threadIdx.x; i < KH * ROWF; i += blockDim.x) {
-    const int ky = i / ROWF, j = i % ROWF;
-    const int x = x_in0 + j / 3, y = y_in0 + ky;
+  const int xo0 = blockIdx.x * TW, yo0 = blockIdx.y * TH, n = blockIdx.z;
+  const int x_in0 = xo0 * 2 - PAD, y_in0 = yo0 * 2 - PAD;
+  for (int i = threadIdx.x; i < ROWS * ROWF; i += blockDim.x) {
+    const int ry = i / ROWF, j = i % ROWF;
+    const int x = x_in0 + j / 3, y = y_in0 + ry;
     float v = 0.f;
     if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(img + (((size_t)n * H + y) * W + x) * 3 + (j % 3));
-    s[ky][j] = v;
+    s[ry][j] = v;
   }
   __syncthreads();
   const int groups = out.C / 8;
-  for (int w = threadIdx.x; w < TW * groups; w += blockDim.x) {
-    const int xl = w / groups, g = w % groups;
-    if (xo0 + xl >= Wo) continue;
+  for (int w = threadIdx.x; w < TH * TW * groups; w += blockDim.x) {
+    const int g = w % groups, pl = w / groups;
+    const int xl = pl % TW, yl = pl / TW;
+    if (xo0 + xl >= Wo || yo0 + yl >= Ho) continue;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = g * 8 + i;
-      v[i] = (k < KTOT) ? s[k / (KW * 3)][xl * 6 + k % (KW * 3)] : 0.f;
+      v[i] = (k < KTOT) ? s[yl * 2 + k / (KW * 3)][xl * 6 + k % (KW * 3)] : 0.f;
     }
-    st_act8(out, ((size_t)n * Ho + yo) * Wo + xo0 + xl, g * 8, v);
+    st_act8(out, ((size_t)n * Ho + yo0 + yl) * Wo + xo0 + xl, g * 8, v);
   }
 }
 
 int launch_im2col_stem(const float* const* img, int N, int H, int W, int kh, int kw, int stride, int pad_t, int pad_l, int Ho,
                        int Wo, Act out, cudaStream_t s) {
   if (stride == 2 && pad_t == pad_l && Ho <= 65535 && N <= 65535) {
-    const dim3 grid((Wo + 63) / 64, Ho, N);
+    const dim3 grid((Wo + 63) / 64, (Ho + 3) / 4, N);
     if (kh == 7 && kw == 7 && pad_t == 3) {
       FPNMT_CUDA_OK(launch_k(k_im2col_stem_s2<7, 7, 3>, grid, dim3(256), 0, s, img, N, H, W, Ho, Wo, out));
       return 0;

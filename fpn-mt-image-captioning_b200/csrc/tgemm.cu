@@ -177,6 +177,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           ++gB;
           tc_fence_after();
           if (g == 0 && rt == rt0) DBG(3);
+          if (rt == rt0 && g < 2) DBG(9 + 2 * g);
           const int n = min(G, kiters - g * G);
           const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA + sa * G * TG_A_BYTES));
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB + sb * G * B_BYTES));
@@ -194,6 +195,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
                 umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
                           IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
           }
+          if (rt == rt0 && g < 2) DBG(10 + 2 * g);
           umma_commit(&emptyB[sb]);
           if (!p.stationary) umma_commit(&emptyA[sa]);
         }
