@@ -29,6 +29,8 @@ struct TgemmParams {
   int ftiles, rtiles;    // ceil(F / 128), ceil(R / BN)
   int rt_per_item;       // row tiles handled by one CTA (consecutive)
   int stationary;        // 1: the weight panel (<= 8 chunks) stays in shared memory for all row tiles of the CTA
+  int ksplit;            // 1, or 2: the K range is split over two CTAs of the (8-CTA) LayerNorm cluster, partial sums
+                         // are added through distributed shared memory (long-K layers: FFN2, K = 2048)
   const float* bias;     // [F] (padded to a multiple of 128) or nullptr
   int act;
   Act out;               // bf16 output view [R][ld] (p may be nullptr)
@@ -47,7 +49,7 @@ struct TgemmOp {
   TgemmParams p;
   int BN;        // 32 or 64
   int grid;
-  int cluster;   // 1 or 4
+  int cluster;   // 1, 4 (LayerNorm) or 8 (LayerNorm + split-K)
   double flops;
 };
 
