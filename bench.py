@@ -372,6 +372,9 @@ def main():
         run_reference(args, wl)
     else:
         run_own(args, wl)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
