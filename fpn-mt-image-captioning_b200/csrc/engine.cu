@@ -63,6 +63,8 @@ int Engine::init() {
   num_sms_ = prop.multiProcessorCount;
   RC(igemm_set_attributes());
   RC(tgemm_set_attributes());
+  RC(xattn_set_attributes());
+  if (const char* e = getenv("FPNMT_XATTN")) use_xattn_ = !(e[0] == '0');
   if (const char* e = getenv("FPNMT_TGEMM")) use_tgemm_ = !(e[0] == '0');
   FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
   FPNMT_CUDA_OK(cudaMallocHost(&h_pinned_, 64));
@@ -808,6 +810,38 @@ int Engine::build_decoder() {
     RC(add_conv(dec_init_prog_, "dec_cross_kv", enc_out_, g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, ckv));
     taps_["cross_kv"] = ckv;
 
+    // Fused cross-attention block (bf16 mode): per-image folded operands, recomputed once per batch (xattn.cuh)
+    const bool xattn = use_xattn_ && use_tgemm_ && !split_ && N <= XA_NROWS && n_base_ <= 16 && D == 512 && H == 8;
+    bf16 *xMt = nullptr, *xNt = nullptr;
+    float* xSb = nullptr;
+    if (xattn) {
+      xMt = (bf16*)dalloc((size_t)L * B * 128 * 512 * 2);
+      xNt = (bf16*)dalloc((size_t)L * B * 512 * 128 * 2);
+      xSb = (float*)dalloc((size_t)L * B * 128 * 4);
+      if (!xMt || !xNt || !xSb) return FPNMT_ERR_CUDA;
+      std::vector<const float*> hq(L), hb(L), ho(L);
+      for (int l = 0; l < L; ++l) {
+        const std::string m = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l) + "/mha2";
+        float *a, *b2, *c;
+        RC(prep_vec(m + "/wq/kernel", &a));
+        RC(prep_vec(m + "/wq/bias", &b2));
+        RC(prep_vec(m + "/dense/kernel", &c));
+        hq[l] = a; hb[l] = b2; ho[l] = c;
+      }
+      const float** dq = (const float**)dalloc(L * sizeof(float*));
+      const float** db = (const float**)dalloc(L * sizeof(float*));
+      const float** d_o = (const float**)dalloc(L * sizeof(float*));
+      FPNMT_CUDA_OK(cudaMemcpy(dq, hq.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
+      FPNMT_CUDA_OK(cudaMemcpy(db, hb.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
+      FPNMT_CUDA_OK(cudaMemcpy(d_o, ho.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
+      Act ca = ckv.a;
+      const int nm = n_base_;
+      Op o = ew_op("xattn_fold", [=](cudaStream_t s) { return launch_xattn_fold(ca, B, nm, L, dq, db, d_o, xMt, xNt, xSb, s); },
+                   (double)L * B * 2 * 128 * 512 * 2, "elementwise");
+      o.flops = 2.0 * 2.0 * L * B * 128.0 * 512.0 * 64.0;
+      dec_init_prog_.push_back(std::move(o));
+    }
+
     Tensor x = rows_act(R, D);
     const BeamState bs = bs_;
     // step 0 input (embedding of <start> + pos[0]); later steps' inputs are written by the beam kernel
@@ -860,14 +894,26 @@ int Engine::build_decoder() {
         step_prog_.push_back(std::move(o));
       }
       RC(dense_res_ln(ln + "_o1+res", ln + "_ln1", att, go1, x, lnp[0], lnp[1], out1));
-      RC(dense(ln + "_q2", out1, gq2, ACT_NONE, q2));
-      {
-        Act qa = q2.a, ka = ckv.a, oa = att2.a;
-        const int kcx = l * 2 * D, vcx = l * 2 * D + D, tk = n_base_;
-        step_prog_.push_back(ew_op(ln + "_cross_attn", [=](cudaStream_t s) { return launch_dec_cross_attention(qa, ka, kcx, vcx, R, N, tk, H, oa, s); },
-                                   (double)B * tk * 2 * D * 2, "attention"));
+      if (xattn) {
+        XattnOp xo;
+        RC(make_xattn_op(&xo, xMt, xNt, L, B, N, l, xSb, go2.bias, lnp[2], lnp[3], out1.a, out2.a));
+        Op o;
+        o.name = ln + "_xattn(q2+cross_attn+o2+res+ln)";
+        o.kind = "xattn";
+        o.flops = 2.0 * R * D * D * 2.0 + 4.0 * R * n_base_ * D;          // the two projections + the attention proper
+        o.bytes = (double)B * 2 * 128 * 512 * 2 + (double)R * D * 2 * 2;   // folded per-image operands + activations
+        o.run = [xo](cudaStream_t s) { return xattn_launch(xo, s); };
+        step_prog_.push_back(std::move(o));
+      } else {
+        RC(dense(ln + "_q2", out1, gq2, ACT_NONE, q2));
+        {
+          Act qa = q2.a, ka = ckv.a, oa = att2.a;
+          const int kcx = l * 2 * D, vcx = l * 2 * D + D, tk = n_base_;
+          step_prog_.push_back(ew_op(ln + "_cross_attn", [=](cudaStream_t s) { return launch_dec_cross_attention(qa, ka, kcx, vcx, R, N, tk, H, oa, s); },
+                                     (double)B * tk * 2 * D * 2, "attention"));
+        }
+        RC(dense_res_ln(ln + "_o2+res", ln + "_ln2", att2, go2, out1, lnp[2], lnp[3], out2));
       }
-      RC(dense_res_ln(ln + "_o2+res", ln + "_ln2", att2, go2, out1, lnp[2], lnp[3], out2));
       RC(dense(ln + "_ffn1", out2, g1, ACT_LEAKY, hdn));
       RC(dense_res_ln(ln + "_ffn2+res", ln + "_ln3", hdn, g2, out2, lnp[4], lnp[5], out3));
       x = out3;

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "tensormap.cuh"
 #include "tgemm.cuh"
+#include "xattn.cuh"
 
 namespace fpnmt {
 
@@ -115,6 +116,7 @@ class Engine {
   int add_dense(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int act, const Tensor* res,
                 const Tensor& out, float* out_f32 = nullptr, int ld_f32 = 0, const float* gamma = nullptr,
                 const float* beta = nullptr);
+  bool use_xattn_ = true;                 // FPNMT_XATTN=0: separate q2 / cross-attention / o2+LN kernels (always in BF16X3 mode)
   bool use_tgemm_ = true;                 // FPNMT_TGEMM=0 routes the decoder GEMMs through igemm + separate LayerNorm
   int build_stem_resnet_like(Program& p, const std::string& conv_key, const std::string& bn_key, float eps, Tensor* out);
   int build_resnet50(Program& p, Tensor c[3]);

@@ -1,0 +1,390 @@
+// Fused decoder cross-attention block (see xattn.cuh).  One CTA per image:
+//   warp 0     : TMA producer.  Mt_b (128 x 512, 8 chunks) and the first two feature tiles of Nt_b are per-batch constants
+//                and are fetched BEFORE griddepcontrol.wait; only the 16 x 512 activation rows depend on the previous kernel.
+//   warp 1     : MMA issuer.  chain 1: S^T[128 (h,j) x 16 rows] = Mt_b . out1^T   (32 tcgen05.mma, N = 16)
+//                             chain 2: O^T[4 x 128 features x 16 rows] = Nt_b . P^T (4 x 8 tcgen05.mma)
+//   warps 2..5 : softmax over the 16 memory tokens (16-lane shuffle groups on the TMEM-loaded scores), P^T -> shared
+//                memory (K-major, 128B swizzle, UMMA B operand), then bias + residual + LayerNorm of the output rows.
+#include "xattn.cuh"
+
+#include "tensormap.cuh"
+
+namespace fpnmt {
+
+constexpr int XA_CHUNK_A = 128 * 64 * 2;                 // 16 KB: 128 rows x 64 K
+constexpr int XA_CHUNK_B = XA_NROWS * 64 * 2;            // 2 KB: 16 rows x 64 K
+constexpr int XA_OFF_A1 = 0;                             // 8 chunks (Mt_b); later the LayerNorm scratch
+constexpr int XA_OFF_A2 = 8 * XA_CHUNK_A;                // 4 chunks (two feature tiles of Nt_b in flight)
+constexpr int XA_OFF_B1 = XA_OFF_A2 + 4 * XA_CHUNK_A;    // 8 chunks (out1 rows)
+constexpr int XA_OFF_B2 = XA_OFF_B1 + 8 * XA_CHUNK_B;    // 2 chunks (P^T)
+constexpr int XA_OFF_PART = XA_OFF_B2 + 2 * XA_CHUNK_B;  // float2 [8][16]
+constexpr int XA_OFF_BARS = XA_OFF_PART + 8 * 16 * 8;
+constexpr int XA_SCR_STRIDE = 513;                       // floats per row of the transposed output scratch
+constexpr int XA_TMEM_COLS = 128;
+
+size_t xattn_smem_bytes() { return XA_OFF_BARS + 256 + 1024; }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(XA_THREADS, 1)
+xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+             const __grid_constant__ CUtensorMap tmX, const XattnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA1 = smem + XA_OFF_A1;
+  uint8_t* sA2 = smem + XA_OFF_A2;
+  uint8_t* sB1 = smem + XA_OFF_B1;
+  uint8_t* sB2 = smem + XA_OFF_B2;
+  float2* sPart = reinterpret_cast<float2*>(smem + XA_OFF_PART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XA_OFF_BARS);
+  uint64_t* fullA1 = bars;          // Mt_b landed
+  uint64_t* fullB1 = bars + 1;      // out1 rows landed
+  uint64_t* fullA2 = bars + 2;      // [4] feature tile ft of Nt_b landed
+  uint64_t* emptyA2 = bars + 6;     // [2] slot pair free again
+  uint64_t* tfull1 = bars + 8;      // scores ready
+  uint64_t* pready = bars + 9;      // P^T written (128 arrivals)
+  uint64_t* tfull2 = bars + 10;     // outputs ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int opnd = p.layer * p.B + b;                 // which per-image operand set
+
+  pdl_launch();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmM);
+    tma_prefetch_desc(&tmN);
+    tma_prefetch_desc(&tmX);
+    mbar_init(fullA1, 1);
+    mbar_init(fullB1, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&fullA2[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&emptyA2[i], 1);
+    mbar_init(tfull1, 1);
+    mbar_init(pready, 128);
+    mbar_init(tfull2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<XA_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, XA_NROWS);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // per-batch constants: before the grid dependency resolves
+      mbar_expect_tx(fullA1, 8 * XA_CHUNK_A);
+      for (int i = 0; i < 8; ++i) tma_load_2d(sA1 + i * XA_CHUNK_A, &tmM, fullA1, i * 64, opnd * 128);
+      for (int ft = 0; ft < 2; ++ft) {
+        mbar_expect_tx(&fullA2[ft], 2 * XA_CHUNK_A);
+        for (int c = 0; c < 2; ++c)
+          tma_load_2d(sA2 + (ft * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128);
+      }
+      pdl_wait();
+      mbar_expect_tx(fullB1, 8 * XA_CHUNK_B);
+      for (int i = 0; i < 8; ++i) tma_load_2d(sB1 + i * XA_CHUNK_B, &tmX, fullB1, i * 64, b * p.beam);
+      // feature tiles 2,3 of Nt_b go into the upper half of the Mt_b area as soon as chain 1 has consumed it, so their
+      // load latency overlaps the softmax instead of sitting between the two MMA chains
+      mbar_wait(tfull1, 0);
+      for (int ft = 2; ft < 4; ++ft) {
+        mbar_expect_tx(&fullA2[ft], 2 * XA_CHUNK_A);
+        for (int c = 0; c < 2; ++c)
+          tma_load_2d(sA1 + (4 + (ft - 2) * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- chain 1: scores^T
+      mbar_wait(fullA1, 0);
+      mbar_wait(fullB1, 0);
+      tc_fence_after();
+      {
+        const uint64_t a0 = umma_desc_sw128(smem_u32(sA1));
+        const uint64_t b0 = umma_desc_sw128(smem_u32(sB1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, a0 + (uint64_t)(i * (XA_CHUNK_A >> 4) + 2 * k), b0 + (uint64_t)(i * (XA_CHUNK_B >> 4) + 2 * k), IDESC,
+                      (i > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(tfull1);
+      // ---- chain 2: outputs^T, four feature tiles of 128
+      mbar_wait(pready, 0);
+      tc_fence_after();
+      const uint64_t pb0 = umma_desc_sw128(smem_u32(sB2));
+      for (int ft = 0; ft < 4; ++ft) {
+        mbar_wait(&fullA2[ft], 0);
+        tc_fence_after();
+        const uint64_t a0 = umma_desc_sw128(smem_u32(ft < 2 ? sA2 + ft * 2 * XA_CHUNK_A : sA1 + (4 + (ft - 2) * 2) * XA_CHUNK_A));
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + 32 + ft * XA_NROWS, a0 + (uint64_t)(c * (XA_CHUNK_A >> 4) + 2 * k),
+                      pb0 + (uint64_t)(c * (XA_CHUNK_B >> 4) + 2 * k), IDESC, (c > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(tfull2);
+    }
+    __syncwarp();
+  } else {
+    const int e = warp - 2;                       // 0..3
+    const int quarter = warp & 3;                 // TMEM lane window
+    const int L = quarter * 32 + lane;            // (head, token) pair == TMEM lane == K index of chain 2
+    const int t = e * 32 + lane;                  // 0..127
+    const int lrow = t & 15, part = t >> 4;       // LayerNorm phase: row of the image, 64-feature slice
+    const float sb = __ldg(p.sbias + (size_t)opnd * XA_PAIRS + L);
+    pdl_wait();
+    const int grow = b * p.beam + lrow;           // global row handled in the LayerNorm phase
+    const bool row_ok = lrow < p.beam && grow < p.R;
+    uint4 rres[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) rres[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok) {                                 // residual = out1 row slice: in flight during both MMA chains
+      const bf16* q = p.res.p + (size_t)grow * p.res.ld + part * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) rres[g] = *reinterpret_cast<const uint4*>(q + g * 8);
+    }
+    // ---- softmax over the 16 tokens of this head, for each of the 16 row columns
+    mbar_wait(tfull1, 0);
+    tc_fence_after();
+    {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16), r);
+      tmem_ld_wait();
+      float pr[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c >= p.beam) {                        // padding columns (rows of the next image): never read back
+          pr[c] = 0.f;
+          continue;
+        }
+        const float s = __uint_as_float(r[c]) + sb;
+        float m = s;
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        const float ex = __expf(s - m);
+        float sum = ex;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        pr[c] = ex / sum;
+      }
+      // P^T[row c][k = L]: K-major rows of 128 B, 16-byte units XOR-swizzled with (row & 7)
+      uint8_t* base = sB2 + (L >> 6) * XA_CHUNK_B + (L & 7) * 2;
+      const int unit = (L & 63) >> 3;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        *reinterpret_cast<bf16*>(base + c * 128 + ((unit ^ (c & 7)) << 4)) = __float2bfloat16_rn(pr[c]);
+    }
+    fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
+    mbar_arrive(pready);
+    // ---- outputs: + bias, transpose through the scratch (aliases the Mt_b area, free since chain 1 completed)
+    float* scr = reinterpret_cast<float*>(sA1);
+    mbar_wait(tfull2, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ft = 0; ft < 4; ++ft) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + 32 + ft * XA_NROWS, r);
+      tmem_ld_wait();
+      const int f = ft * 128 + L;
+      const float ob = __ldg(p.obias + f);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) scr[c * XA_SCR_STRIDE + f] = __uint_as_float(r[c]) + ob;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---- residual + LayerNorm over 512 features: 8 threads per row, 64 features each (Chan's parallel variance)
+    float x[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) x[i] = scr[lrow * XA_SCR_STRIDE + part * 64 + i];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float tt[8];
+      unpack8(rres[g], tt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[g * 8 + i] += tt[i];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) sum += x[i];
+    const float mloc = sum * (1.f / 64.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const float d = x[i] - mloc;
+      m2 = fmaf(d, d, m2);
+    }
+    sPart[part * 16 + lrow] = make_float2(mloc, m2);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float mean = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mean += sPart[q * 16 + lrow].x;
+    mean *= 0.125f;
+    float M2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 a = sPart[q * 16 + lrow];
+      const float d = a.x - mean;
+      M2 += a.y + 64.f * d * d;
+    }
+    const float rstd = rsqrtf(M2 * (1.f / 512.f) + p.eps);
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int f0 = part * 64 + g * 8;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + f0));
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gamma + f0 + 4));
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + f0));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + f0 + 4));
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (x[g * 8 + i] - mean) * rstd * gg[i] + be[i];
+        st_act8(p.out, (size_t)grow, f0, o);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<XA_TMEM_COLS>(tmem_base);
+  }
+}
+
+int xattn_set_attributes() {
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(xattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes()));
+  return 0;
+}
+
+int xattn_launch(const XattnOp& op, cudaStream_t stream) {
+  FPNMT_CUDA_OK(launch_k(xattn_kernel, dim3(op.p.B), dim3(XA_THREADS), xattn_smem_bytes(), stream, op.tmM, op.tmN, op.tmX, op.p));
+  return 0;
+}
+
+int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int beam, int layer, const float* sbias,
+                  const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out) {
+  if (beam > XA_NROWS || x.C != 512 || x.lo || out.lo) {
+    set_last_error("make_xattn_op: needs beam <= 16, d_model == 512 and plain bf16 activations");
+    return 1;
+  }
+  XattnParams& p = op->p;
+  p = XattnParams{};
+  p.B = B;
+  p.beam = beam;
+  p.R = B * beam;
+  p.layer = layer;
+  p.sbias = sbias;
+  p.obias = obias;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.eps = 1e-6f;
+  p.res = x;
+  p.out = out;
+  int rc = encode_tmap_2d(&op->tmM, Mt, 512, (uint64_t)L * B * 128, 512, 128);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&op->tmN, Nt, 128, (uint64_t)L * B * 512, 128, 128);
+  if (rc) return rc;
+  return encode_tmap_2d(&op->tmX, x.p, 512, (uint64_t)B * beam, (uint64_t)x.ld, XA_NROWS);
+}
+
+// ------------------------------------------------------------------------------------------------ folding kernels
+// grid (B, heads = 8, L), 256 threads.  Keys/values of one (image, head, layer) are staged in shared memory as fp32.
+__global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const float* const* __restrict__ wq,
+                                                      const float* const* __restrict__ bq, bf16* __restrict__ Mt,
+                                                      float* __restrict__ sbias) {
+  __shared__ float sK[16][65];
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
+  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+    const int j = i >> 6, d = i & 63;
+    sK[j][d] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + h * 64 + d]) : 0.f;
+  }
+  __syncthreads();
+  const float* W = wq[l];                       // Dense kernel (in = k, out = h*64+d), row-major
+  bf16* dst = Mt + ((size_t)(l * B + b) * 128 + h * 16) * 512;
+  for (int k = threadIdx.x; k < 512; k += blockDim.x) {
+    float w[64];
+#pragma unroll
+    for (int d4 = 0; d4 < 16; ++d4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * 512 + h * 64 + d4 * 4));
+      w[4 * d4] = v.x; w[4 * d4 + 1] = v.y; w[4 * d4 + 2] = v.z; w[4 * d4 + 3] = v.w;
+    }
+    for (int j = 0; j < 16; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) a = fmaf(sK[j][d], w[d], a);
+      dst[(size_t)j * 512 + k] = __float2bfloat16_rn(a * 0.125f);
+    }
+  }
+  if (threadIdx.x < 16) {
+    const int j = threadIdx.x;
+    float a = 0.f;
+    for (int d = 0; d < 64; ++d) a = fmaf(sK[j][d], __ldg(bq[l] + h * 64 + d), a);
+    sbias[(size_t)(l * B + b) * 128 + h * 16 + j] = j < n_mem ? a * 0.125f : -1e30f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int n_mem, const float* const* __restrict__ wo,
+                                                      bf16* __restrict__ Nt) {
+  __shared__ float sV[16][65];
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
+  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+    const int j = i >> 6, d = i & 63;
+    sV[j][d] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
+  }
+  __syncthreads();
+  const float* W = wo[l];                       // Dense kernel (in = h*64+d, out = f), row-major
+  for (int f = threadIdx.x; f < 512; f += blockDim.x) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int d = 0; d < 64; ++d) {
+      const float w = __ldg(W + (size_t)(h * 64 + d) * 512 + f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(sV[j][d], w, acc[j]);
+    }
+    bf16* dst = Nt + ((size_t)(l * B + b) * 512 + f) * 128 + h * 16;
+    uint4 o0 = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+    uint4 o1 = make_uint4(pack2(acc[8], acc[9]), pack2(acc[10], acc[11]), pack2(acc[12], acc[13]), pack2(acc[14], acc[15]));
+    *reinterpret_cast<uint4*>(dst) = o0;
+    *reinterpret_cast<uint4*>(dst + 8) = o1;
+  }
+}
+
+__global__ void k_xattn_fence() {}
+
+int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const float* const* wq, const float* const* bq,
+                      const float* const* wo, bf16* Mt, bf16* Nt, float* sbias, cudaStream_t s) {
+  if (n_mem > 16 || ckv.lo) {
+    set_last_error("xattn_fold: at most 16 memory tokens, plain bf16 K/V");
+    return 1;
+  }
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_q, dim3(B, 8, L), dim3(256), 0, s, ckv, n_mem, wq, bq, Mt, sbias));
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_o, dim3(B, 8, L), dim3(256), 0, s, ckv, n_mem, wo, Nt));
+  // A launch WITHOUT the programmatic-serialization attribute: it starts only after the fold kernels have completed
+  // and been flushed, so later kernels (which prefetch Mt / Nt before their griddepcontrol.wait) can never overtake them.
+  k_xattn_fence<<<1, 32, 0, s>>>();
+  FPNMT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fpnmt

@@ -231,3 +231,33 @@ def test_encoder_attention_mma_matches_simt_path():
     os.environ.pop("FPNMT_ENC_ATT_SIMT", None)
     for l in range(L):
         assert rel(outs["0"][l], outs["1"][l]) < 2e-2, (l, rel(outs["0"][l], outs["1"][l]))
+
+
+@pytest.mark.parametrize("size", [512, 256])
+def test_fused_cross_attention_block_matches_unfused_path(size):
+    """bf16 mode: xattn_kernel (folded Q/O projections + softmax over the memory tokens + residual + LayerNorm in one
+    tcgen05 kernel) vs the three separate kernels on the same weights / memory / tokens.  512x512 has 16 memory tokens,
+    256x256 has 4 (exercises the padded-token mask).  Differences: the folded operands are rounded to bf16 once more and
+    P is bf16 -> teacher-forced logits within 5e-2 relative L2, arg-max agreement >= 90 %."""
+    import os
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=12)
+    img = O.test_images(B, size, seed=3)
+    gtok = torch.randint(4, V, (B, T), generator=torch.Generator().manual_seed(5))
+    gtok[:, 0] = 2
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["FPNMT_XATTN"] = mode
+        eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=size, precision="bf16",
+                     use_graphs=False)
+        eng.encode(img.cuda())
+        outs[mode] = eng.decode_logits(None, gtok.int().cuda()).cpu()
+        ids, lens = eng.generate(img.cuda(), early_stop=False)
+        outs["ids" + mode] = ids.clone()
+        eng.close()
+    os.environ.pop("FPNMT_XATTN", None)
+    err = rel(outs["1"], outs["0"])
+    agree = float((outs["1"].argmax(-1) == outs["0"].argmax(-1)).float().mean())
+    assert err < 5e-2 and agree >= 0.9, (size, err, agree)
+    assert torch.isfinite(outs["1"]).all()

@@ -187,7 +187,8 @@ for r in range(world):
     assert (alllens[r * b:(r + 1) * b] == r + 1).all()
 assert fd.max_over_ranks(float(rank)) == world - 1
 lo, hi = fd.shard_bounds(10, rank, world)
-print("rank", rank, "ok", lo, hi)
+sys.stdout.write("rank %%d ok %%d %%d\n" %% (rank, lo, hi))   # one write per rank: lines cannot interleave
+sys.stdout.flush()
 '''
 
 
