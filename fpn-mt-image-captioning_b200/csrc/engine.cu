@@ -1197,7 +1197,7 @@ int Engine::profile(int iters, char* buf, size_t cap) {
   if (dbg_buf_) {   // FPNMT_DBG_OP timeline of the last 8 instances (ns relative to each instance's entry)
     long long h[16 * 9];
     cudaMemcpy(h, dbg_buf_, sizeof h, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[fpnmt dbg] %lld instances; stamps: entry setup pdl_wait first_full mma_issued tfull epi_chunk0 epi_chunk1 end g0_ready g0_issued g1_ready g1_issued\n", h[0]);
+    fprintf(stderr, "[fpnmt dbg] %lld instances; stamps: entry setup pdl_wait first_full mma_issued tfull epi_chunk0 epi_chunk1 end tile1_start tile2_start tile3_start tile4_start\n", h[0]);
     for (int i = 0; i < 8; ++i) {
       const long long* t = h + 16 + i * 16;
       fprintf(stderr, "[fpnmt dbg] inst slot %d entry@%lld:", i, t[0]);

@@ -191,7 +191,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           ++gB;
           tc_fence_after();
           if (g == 0 && rt == rt0) DBG(3);
-          if (rt == rt0 && g < 2) DBG(9 + 2 * g);
+          if (g == 0 && rt > rt0 && rt - rt0 <= 4) DBG(8 + (rt - rt0));
           const int n = min(G, kiters - (g_begin + g) * G);
           const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA + sa * G * TG_A_BYTES));
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB + sb * G * B_BYTES));
@@ -209,7 +209,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
                 umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
                           IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
           }
-          if (rt == rt0 && g < 2) DBG(10 + 2 * g);
           umma_commit(&emptyB[sb]);
           if (!p.stationary) umma_commit(&emptyA[sa]);
         }
@@ -235,6 +234,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
     const int fo = ftile * TG_BM + e * 32;  // phase B: first of this thread's 32 features
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool direct_f32 = !is_ln && p.out_f32 != nullptr && p.out.p == nullptr && !p.has_res && p.act != ACT_RELU6;
     pdl_wait();
     if (helper_b && e == 0 && lane == 0) {
       const int n = kiters - G;
@@ -277,6 +277,35 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           if (ch == CHUNKS - 1) {           // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
+          }
+          if (direct_f32) {
+            // fp32-only output without residual (the vocabulary projection): store straight from the accumulator layout.
+            // Thread = feature, so each of the 32 predicated stores of a warp covers 128 contiguous bytes of one row;
+            // no shared-memory transpose, no barriers.
+            const int rb = rt * BN + ch * 32;
+            float* o = p.out_f32 + (size_t)rb * p.ld_f32 + f;     // running pointer: one 64-bit add per store
+            const size_t ldb = (size_t)p.ld_f32;
+            const int nvalid = (f < p.F) ? min(32, p.R - rb) : 0;  // rows this thread may write
+            if (p.act == ACT_LEAKY) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float v = __uint_as_float(r[c]) + bias;
+                r[c] = __float_as_uint(v >= 0.f ? v : 0.2f * v);
+              }
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaxf(__uint_as_float(r[c]) + bias, 0.f));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + bias);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (c < nvalid) *o = __uint_as_float(r[c]);
+              o += ldb;
+            }
+            if (e == 0 && lane == 0 && rt == rt0) DBG(6 + ch);
+            continue;
           }
 #pragma unroll
           for (int c = 0; c < 32; ++c) sLN[c * TG_LN_STRIDE + fl] = __uint_as_float(r[c]) + bias;
