@@ -42,6 +42,7 @@ Engine::~Engine() {
   if (cnn_graph_) cudaGraphExecDestroy(cnn_graph_);
   if (enc_graph_) cudaGraphExecDestroy(enc_graph_);
   if (step_graph_) cudaGraphExecDestroy(step_graph_);
+  if (loop_graph_) cudaGraphExecDestroy(loop_graph_);
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
   for (void* p : allocs_) cudaFree(p);
@@ -1107,6 +1108,17 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
   launches += 1;
   RC(run_program(dec_init_prog_, s));
   RC(run_program(embed_prog_, s));
+  if (cfg_.use_graphs && !early_stop) {
+    // fixed-length decode: all T steps replay as ONE graph (no per-step graph-launch gap; the programmatic-launch chain
+    // runs across step boundaries)
+    if (!loop_graph_) {
+      Program loop;
+      for (int t = 0; t < T; ++t) loop.insert(loop.end(), step_prog_.begin(), step_prog_.end());
+      RC(capture(loop, &loop_graph_));
+    }
+    FPNMT_CUDA_OK(cudaGraphLaunch(loop_graph_, s));
+    launches += (int64_t)T * (int64_t)step_prog_.size();
+  } else {
   if (cfg_.use_graphs && !step_graph_) RC(capture(step_prog_, &step_graph_));
   for (int t = 0; t < T; ++t) {
     RC(launch_prog(step_prog_, step_graph_, s));
@@ -1115,6 +1127,7 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
       FPNMT_CUDA_OK(cudaStreamSynchronize(s));
       if (h_pinned_[0] >= B) break;
     }
+  }
   }
   const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (out_ids) FPNMT_CUDA_OK(cudaMemcpyAsync(out_ids, bs_.out_ids, (size_t)B * T * 4, kind, s));

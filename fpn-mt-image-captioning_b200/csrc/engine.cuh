@@ -75,7 +75,7 @@ class Engine {
   // programs
   Program cnn_prog_, enc_prog_, dec_init_prog_, embed_prog_, step_prog_, step_forced_prog_;
   BeamEmbed beam_embed_{};
-  cudaGraphExec_t cnn_graph_ = nullptr, enc_graph_ = nullptr, step_graph_ = nullptr;
+  cudaGraphExec_t cnn_graph_ = nullptr, enc_graph_ = nullptr, step_graph_ = nullptr, loop_graph_ = nullptr;
   cudaStream_t cap_stream_ = nullptr;
 
   // buffers referenced at run time
