@@ -216,6 +216,16 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
   return rc;
 }
 
+// ---- input preprocessing operator ------------------------------------------------------------------------
+FPNMT_API int fpnmt_op_preprocess(int device, const uint8_t* images_hwc, int N, int H, int W, int S, float* out, void* stream) {
+  if (!images_hwc || !out || N < 1 || H < 1 || W < 1 || S < 1) {
+    set_last_error("op_preprocess: bad arguments");
+    return FPNMT_ERR_INVALID;
+  }
+  FPNMT_CUDA_OK(cudaSetDevice(device));
+  return launch_preprocess(images_hwc, N, H, W, S, out, (cudaStream_t)stream);
+}
+
 // ---- stand-alone skinny-row Dense operator (tgemm) -----------------------------------------------------
 FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, int K, const float* kernel, int F,
                    const float* bias, int act, const float* residual, const float* gamma, const float* beta, float eps,

@@ -434,6 +434,40 @@ int launch_embed_pos(const int* tokens, const float* emb, const float* pos, cons
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------- input preprocessing
+// dataset.py:19-26 after the JPEG decode: tf.image.resize(img, (S,S)) (bilinear, half-pixel centres, no antialias) and
+// mobilenet_v2.preprocess_input (x / 127.5 - 1).  uint8 HWC in, float32 NHWC in [-1, 1] out; one thread per output pixel.
+__global__ void k_preprocess(const uint8_t* __restrict__ img, int N, int H, int W, int S, float* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * S * S) return;
+  const int x = (int)(idx % S), y = (int)((idx / S) % S), n = (int)(idx / ((size_t)S * S));
+  const float sy = (y + 0.5f) * ((float)H / (float)S) - 0.5f;
+  const float sx = (x + 0.5f) * ((float)W / (float)S) - 0.5f;
+  const float fy0 = floorf(sy), fx0 = floorf(sx);
+  const float wy = sy - fy0, wx = sx - fx0;
+  const int y0 = min(max((int)fy0, 0), H - 1), y1 = min(max((int)fy0 + 1, 0), H - 1);
+  const int x0 = min(max((int)fx0, 0), W - 1), x1 = min(max((int)fx0 + 1, 0), W - 1);
+  const uint8_t* base = img + (size_t)n * H * W * 3;
+  const uint8_t *p00 = base + ((size_t)y0 * W + x0) * 3, *p01 = base + ((size_t)y0 * W + x1) * 3;
+  const uint8_t *p10 = base + ((size_t)y1 * W + x0) * 3, *p11 = base + ((size_t)y1 * W + x1) * 3;
+  float* o = out + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = p00[c], tr = p01[c], bl = p10[c], br = p11[c];
+    const float top = tl * (1.f - wx) + tr * wx;
+    const float bot = bl * (1.f - wx) + br * wx;
+    o[c] = (top * (1.f - wy) + bot * wy) / 127.5f - 1.f;
+  }
+}
+int launch_preprocess(const uint8_t* img, int N, int H, int W, int S, float* out, cudaStream_t s) {
+  const size_t total = (size_t)N * S * S;
+  FPNMT_CUDA_OK(launch_k(k_preprocess, dim3(nblocks(total, 256)), dim3(256), 0, s, img, N, H, W, S, out));
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- conversions
 __global__ void k_f32_to_act(const float* __restrict__ x, size_t rows, int C, Act out) {
   pdl_launch();

@@ -30,6 +30,8 @@ int launch_layernorm_rows(const float* x, int rows, int C, const float* gamma, c
 // Decoder input: out[r] = emb[tok[r]] + pos[*step]
 int launch_embed_pos(const int* tokens, const float* emb, const float* pos, const int* step, int rows, int C, Act out,
                      cudaStream_t s);
+// dataset.py:19-26 minus the JPEG decode: uint8 HWC [N,H,W,3] -> bilinear (TF2 half-pixel) resize to SxS -> x/127.5-1, fp32 NHWC
+int launch_preprocess(const uint8_t* img, int N, int H, int W, int S, float* out, cudaStream_t s);
 // fp32 rows -> activation view (used for uploads / tests)
 int launch_f32_to_act(const float* x, size_t rows, int C, Act out, cudaStream_t s);
 int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s);

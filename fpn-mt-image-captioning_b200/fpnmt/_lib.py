@@ -48,6 +48,7 @@ SIGNATURES = {
     "fpnmt_profile": (_i, [_vp, _i, C.c_char_p, C.c_size_t]),
     "fpnmt_launch_count": (C.c_int64, [_vp]),
     "fpnmt_op_conv2d": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "fpnmt_op_preprocess": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "fpnmt_op_dense": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
 }
 

@@ -226,3 +226,17 @@ def dense(x: torch.Tensor, kernel: np.ndarray, bias: Optional[np.ndarray] = None
                                   None if res is None else res.data_ptr(), ptr(g), ptr(be), eps, out.data_ptr(), force_bn,
                                   _stream_ptr(dev)))
     return out
+
+
+def preprocess(images_u8: torch.Tensor, size: int = cfg.IMAGE_INPUT_SIZE) -> torch.Tensor:
+    """GPU `load_image` after the JPEG decode (dataset.py:21-24): uint8 (N,H,W,3) -> float32 (N,size,size,3) in [-1,1]."""
+    lib = _lib.load()
+    if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[-1] != 3:
+        raise ValueError("images must be uint8 (N,H,W,3)")
+    if images_u8.device.type != "cuda":
+        raise RuntimeError("fpnmt.preprocess needs CUDA tensors; there is no CPU fallback")
+    x = images_u8.contiguous()
+    n, h, w, _ = x.shape
+    out = torch.empty((n, size, size, 3), dtype=torch.float32, device=x.device)
+    _lib.check(lib.fpnmt_op_preprocess(x.device.index or 0, x.data_ptr(), n, h, w, size, out.data_ptr(), _stream_ptr(x.device)))
+    return out

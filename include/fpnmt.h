@@ -138,6 +138,11 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
                     int kh, int kw, int Cout, int pad_top, int pad_left, const float* bias, int act,
                     const float* residual, int res_mode, float* out, int force_bn, void* stream);
 
+/* Replaces: dataset.load_image after the JPEG decode (dataset.py:21-24): tf.image.resize(img, (S, S)) — bilinear,
+ * half-pixel centres, no antialias — followed by mobilenet_v2.preprocess_input (x / 127.5 - 1).
+ * images_hwc DEVICE uint8 [N, H, W, 3]; out DEVICE float32 NHWC [N, S, S, 3] in [-1, 1] (the layout fpnmt_encode takes). */
+FPNMT_API int fpnmt_op_preprocess(int device, const uint8_t* images_hwc, int N, int H, int W, int S, float* out, void* stream);
+
 /* out[r, f] = epilogue( x[r, :] @ kernel[:, f] + bias[f] [+ residual[r, f]] ) with the skinny-row Dense kernel of the
  * decoder step (tf.keras.layers.Dense, models/transformer.py:117-122, 165-168, 211-214, 357): x DEVICE float32 [R, K];
  * kernel HOST float32 (K, F) Keras layout; bias HOST [F] or NULL; residual DEVICE float32 [R, F] or NULL; out DEVICE

@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 __all__ = ["W", "bn_calibration", "tf_same_pad", "conv2d", "depthwise_conv2d", "max_pool", "avg_pool2", "batch_norm",
-           "layer_norm", "dense", "leaky_relu", "relu6", "nhwc_to_nchw", "nchw_to_nhwc", "upsample_like"]
+           "layer_norm", "dense", "leaky_relu", "relu6", "nhwc_to_nchw", "nchw_to_nhwc", "upsample_like", "load_image_array"]
 
 
 class W:
@@ -162,3 +162,23 @@ def upsample_like(src: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     iy = torch.clamp(torch.floor((torch.arange(hout, dtype=torch.float64) + 0.5) * (hin / hout)).long(), max=hin - 1)
     ix = torch.clamp(torch.floor((torch.arange(wout, dtype=torch.float64) + 0.5) * (win / wout)).long(), max=win - 1)
     return src[:, :, iy][:, :, :, ix]
+
+
+def load_image_array(img_hwc_u8: np.ndarray, size: int = 512) -> np.ndarray:
+    """dataset.py:19-26 after `tf.image.decode_jpeg`: `tf.image.resize(img, (size, size))` (TF2 default: bilinear with
+    half-pixel centres, antialias=False; source index = (dst + 0.5) * scale - 0.5, neighbours clamped to the image) and
+    `mobilenet_v2.preprocess_input` (x / 127.5 - 1).  uint8 (H,W,3) -> float32 (size,size,3) in [-1, 1]."""
+    a = np.asarray(img_hwc_u8).astype(np.float32)
+    h, w = a.shape[0], a.shape[1]
+
+    def axis(n_in, n_out):
+        s = (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) * np.float32(n_in / n_out) - np.float32(0.5)
+        lo = np.floor(s)
+        return (np.clip(lo, 0, n_in - 1).astype(np.int64), np.clip(lo + 1, 0, n_in - 1).astype(np.int64),
+                (s - lo).astype(np.float32))
+    y0, y1, fy = axis(h, size)
+    x0, x1, fx = axis(w, size)
+    fx_, fy_ = fx[None, :, None], fy[:, None, None]
+    top = a[y0][:, x0] * (1 - fx_) + a[y0][:, x1] * fx_
+    bot = a[y1][:, x0] * (1 - fx_) + a[y1][:, x1] * fx_
+    return ((top * (1 - fy_) + bot * fy_) / np.float32(127.5) - np.float32(1.0)).astype(np.float32)

@@ -221,9 +221,31 @@ def model_goldens(out: dict):
     out["predict_tf_logits_rows"] = np.asarray(logits)[0, :, ::4].copy()
 
 
+def load_image_golden(out: dict):
+    """dataset.load_image (dataset.py:19-26) as written, with the two file-system / JPEG primitives replaced by an
+    in-memory uint8 array (the shim has no JPEG decoder); what is pinned is resize -> preprocess_input and dtypes."""
+    import dataset as D   # reference module
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(300, 420, 3), dtype=np.uint8)
+    tf.io.read_file = lambda path: path
+    tf.image.decode_jpeg = lambda data, channels=3: tf.constant(img)
+    res, cap = D.load_image("synthetic.jpg", "a caption")
+    assert cap == "a caption"
+    out["load_image_input_u8"] = img
+    out["load_image_out_sub"] = np.asarray(res).astype(np.float32)[::3, ::3].copy()
+    out["load_image_out_minmax"] = np.array([float(np.asarray(res).min()), float(np.asarray(res).max())], np.float32)
+    # an upsampling case as well (smaller than the target)
+    img2 = rng.integers(0, 256, size=(97, 64, 3), dtype=np.uint8)
+    tf.image.decode_jpeg = lambda data, channels=3: tf.constant(img2)
+    res2, _ = D.load_image("synthetic2.jpg", None)
+    out["load_image_input2_u8"] = img2
+    out["load_image_out2_sub"] = np.asarray(res2).astype(np.float32)[::7, ::5].copy()
+
+
 def main():
     unit, model = {}, {}
     unit_goldens(unit)
+    load_image_golden(unit)
     np.savez_compressed(os.path.join(HERE, "reference_units.npz"), **unit)
     model_goldens(model)
     np.savez_compressed(os.path.join(HERE, "reference_model.npz"), **model)

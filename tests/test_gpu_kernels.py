@@ -185,3 +185,17 @@ def test_tgemm_dense(case, prec, tol):
     err = float((y.double() - ref).norm() / ref.norm())
     assert err < tol, (name, prec, err)
     assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 420), (1, 97, 64), (3, 512, 512), (1, 1080, 1920)])
+def test_preprocess_resize_normalize(shape):
+    """GPU input preprocessing (dataset.py:21-24) vs the oracle on the same uint8 images: <= 2e-5 absolute."""
+    from fpnmt.engine import preprocess
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    out = preprocess(img.cuda(), 512).cpu().numpy()
+    for i in range(n):
+        ref = O.load_image_array(img[i].numpy(), 512)
+        assert np.abs(out[i] - ref).max() < 2e-5
+    assert out.min() >= -1.0 - 1e-6 and out.max() <= 1.0 + 1e-6

@@ -154,3 +154,18 @@ def test_teacher_forced_logits(model, model_run):
     got = logits[0, :, ::4].numpy()
     assert np.abs(got - model["predict_tf_logits_rows"]).max() < 2e-3     # the north-star bound on per-step log-probs
     assert rel(got, model["predict_tf_logits_rows"]) < 2e-4
+
+
+def test_load_image_resize_and_preprocess(units):
+    """dataset.py:19-26 (minus the JPEG decode) as executed by the reference vs the oracle and the host mirror."""
+    from fpnmt.dataset import preprocess_input, resize_bilinear_tf2
+    img = units["load_image_input_u8"]
+    ref = units["load_image_out_sub"]
+    got = O.load_image_array(img, 512)
+    assert got.shape == (512, 512, 3) and got.dtype == np.float32
+    assert np.abs(got[::3, ::3] - ref).max() < 2e-5
+    assert units["load_image_out_minmax"][0] >= -1.0 and units["load_image_out_minmax"][1] <= 1.0
+    host = preprocess_input(resize_bilinear_tf2(img.astype(np.float32), 512, 512))
+    assert np.abs(host[::3, ::3] - ref).max() < 2e-5
+    got2 = O.load_image_array(units["load_image_input2_u8"], 512)[::7, ::5]
+    assert np.abs(got2 - units["load_image_out2_sub"]).max() < 2e-5
