@@ -332,15 +332,23 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
             continue;
           }
         }
+        if (p.has_res) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float t[8];
-          unpack8(rh[g], t);
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            unpack8(rh[g], t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[g * 8 + i] += t[i];
-          unpack8(rl[g], t);
+            for (int i = 0; i < 8; ++i) x[g * 8 + i] += t[i];
+          }
+          if (p.res.lo) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[g * 8 + i] += t[i];
+            for (int g = 0; g < 4; ++g) {
+              float t[8];
+              unpack8(rl[g], t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[g * 8 + i] += t[i];
+            }
+          }
         }
         if (!is_ln) {
           if (p.act == ACT_RELU) {

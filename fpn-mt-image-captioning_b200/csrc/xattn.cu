@@ -308,7 +308,7 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int
 __global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const float* const* __restrict__ wq,
                                                       const float* const* __restrict__ bq, bf16* __restrict__ Mt,
                                                       float* __restrict__ sbias) {
-  __shared__ float sK[16][65];
+  __shared__ __align__(16) float sK[16][64];
   pdl_launch();
   pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
@@ -329,7 +329,13 @@ __global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const 
     for (int j = 0; j < 16; ++j) {
       float a = 0.f;
 #pragma unroll
-      for (int d = 0; d < 64; ++d) a = fmaf(sK[j][d], w[d], a);
+      for (int d4 = 0; d4 < 16; ++d4) {                      // broadcast 16-byte shared loads
+        const float4 kq = *reinterpret_cast<const float4*>(&sK[j][d4 * 4]);
+        a = fmaf(kq.x, w[4 * d4], a);
+        a = fmaf(kq.y, w[4 * d4 + 1], a);
+        a = fmaf(kq.z, w[4 * d4 + 2], a);
+        a = fmaf(kq.w, w[4 * d4 + 3], a);
+      }
       dst[(size_t)j * 512 + k] = __float2bfloat16_rn(a * 0.125f);
     }
   }
@@ -343,13 +349,13 @@ __global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const 
 
 __global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int n_mem, const float* const* __restrict__ wo,
                                                       bf16* __restrict__ Nt) {
-  __shared__ float sV[16][65];
+  __shared__ __align__(16) float sV[64][16];              // [d][j]: the 16 tokens of one d are one 64-byte row
   pdl_launch();
   pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
   for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
     const int j = i >> 6, d = i & 63;
-    sV[j][d] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
+    sV[d][j] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
   }
   __syncthreads();
   const float* W = wo[l];                       // Dense kernel (in = h*64+d, out = f), row-major
@@ -357,10 +363,17 @@ __global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int n_mem, const 
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 4
     for (int d = 0; d < 64; ++d) {
       const float w = __ldg(W + (size_t)(h * 64 + d) * 512 + f);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(sV[j][d], w, acc[j]);
+      for (int j4 = 0; j4 < 4; ++j4) {                       // broadcast 16-byte shared loads
+        const float4 vq = *reinterpret_cast<const float4*>(&sV[d][j4 * 4]);
+        acc[4 * j4] = fmaf(vq.x, w, acc[4 * j4]);
+        acc[4 * j4 + 1] = fmaf(vq.y, w, acc[4 * j4 + 1]);
+        acc[4 * j4 + 2] = fmaf(vq.z, w, acc[4 * j4 + 2]);
+        acc[4 * j4 + 3] = fmaf(vq.w, w, acc[4 * j4 + 3]);
+      }
     }
     bf16* dst = Nt + ((size_t)(l * B + b) * 512 + f) * 128 + h * 16;
     uint4 o0 = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));

@@ -13,6 +13,8 @@ Tolerances (stated here, checked below):
                        Decoder (fed with the oracle's memory): log-probs within 0.25 absolute at logit std ~6,
                        per-step arg-max agreement >= 85 %.  Sequence identity is NOT required.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -261,3 +263,68 @@ def test_fused_cross_attention_block_matches_unfused_path(size):
     agree = float((outs["1"].argmax(-1) == outs["0"].argmax(-1)).float().mean())
     assert err < 5e-2 and agree >= 0.9, (size, err, agree)
     assert torch.isfinite(outs["1"]).all()
+
+
+def test_c1_greedy_single_image_resnet50_matches_faithful_reference_loop():
+    """BASELINE config C1 shape: ResNet-50-FPN, greedy (beam 1), batch 1, 512x512 — token ids identical to the
+    line-by-line restatement of Pipeline.predict (uncached, probability-product scores)."""
+    from fpnmt.engine import Engine
+    bb = "resnet50"
+    w = small_weights(bb, V, L, seed=21)
+    img = O.test_images(1, 512, seed=13)
+    eng = Engine(w, backbone=bb, batch=1, beam=1, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16x3",
+                 score_mode="prob", use_graphs=True)
+    ids, lens = eng.generate(img.cuda(), early_stop=True)
+    eng.close()
+    ref = O.predict_reference(img[0], O.W(w), T, 1, 2, 3, bb, num_layers=L, mode="prob")
+    assert lens[0] == len(ref) and ids[0, :lens[0]].tolist() == ref.tolist()
+
+
+@pytest.mark.parametrize("beam", [3, 16])
+def test_fused_cross_attention_other_beam_widths(beam):
+    """xattn_kernel pads the beam rows of an image to 16 MMA columns: odd and maximal widths vs the unfused path."""
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=14)
+    img = O.test_images(3, 256, seed=2)
+    gtok = torch.randint(4, V, (3, T), generator=torch.Generator().manual_seed(6))
+    gtok[:, 0] = 2
+    outs = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["FPNMT_XATTN"] = mode
+            eng = Engine(w, backbone=bb, batch=3, beam=beam, vocab=V, max_len=T, num_layers=L, image_size=256,
+                         precision="bf16", use_graphs=False)
+            eng.encode(img.cuda())
+            outs[mode] = eng.decode_logits(None, gtok.int().cuda()).cpu()
+            ids, lens = eng.generate(img.cuda(), early_stop=False)
+            outs["ids" + mode] = ids
+            eng.close()
+    finally:
+        os.environ.pop("FPNMT_XATTN", None)
+    assert rel(outs["1"], outs["0"]) < 5e-2
+    assert (outs["ids1"] == outs["ids0"]).float().mean() >= 0.7
+
+
+def test_engine_error_paths():
+    """The C ABI reports misuse through error codes / FpnmtError; nothing falls back silently."""
+    from fpnmt._lib import FpnmtError
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = dict(small_weights(bb, V, L, seed=1))
+    eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=256)
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros(B, 128, 128, 3).cuda())                     # wrong spatial size
+    with pytest.raises(FpnmtError):
+        eng.decode_logits(None, torch.zeros(B, T + 5, dtype=torch.int32).cuda())   # t > max_len
+    with pytest.raises(FpnmtError):
+        eng.tap("no_such_layer")
+    eng.close()
+    w.pop("transformer/final_layer/kernel")
+    with pytest.raises(FpnmtError) as ei:
+        Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=256)
+    assert "final_layer" in str(ei.value)
+    with pytest.raises(FpnmtError):
+        Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=64, vocab=V, max_len=T, num_layers=L, image_size=256)
+    with pytest.raises(FpnmtError):
+        Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=300)

@@ -4,6 +4,7 @@ under profiles/.  Needs only the `ncu` CLI (no GPU).
 
     python tools/ncu_summary.py traffic  <rep> <per-op-profile.json> <out.json>   # DRAM bytes per igemm launch, by op name
     python tools/ncu_summary.py details  <rep> <out.txt>                          # key metrics of every captured launch
+    python tools/ncu_summary.py kernels  <rep> <out.json> [note]                  # mean time + DRAM bytes per kernel name
 """
 import csv
 import io
@@ -44,6 +45,24 @@ def main():
         json.dump({"source": rep, "note": "ncu, one launch each, cold cache, --clock-control none; dram_bytes = "
                    "dram__bytes.sum.per_second x gpu__time_duration", "ops": table}, open(dst, "w"), indent=1)
         print("wrote", dst, len(table), "ops")
+    elif mode == "kernels":
+        rep, dst = sys.argv[2:4]
+        note = sys.argv[4] if len(sys.argv) > 4 else ""
+        hdr, units, rows = raw(rep)
+        ib, it, ik = hdr.index("dram__bytes.sum.per_second"), hdr.index("gpu__time_duration.sum"), hdr.index("Kernel Name")
+        scale = {"Tbyte/s": 1e12, "Gbyte/s": 1e9, "Mbyte/s": 1e6, "Kbyte/s": 1e3, "byte/s": 1.0}[units[ib]]
+        assert units[it] == "us"
+        acc = {}
+        for r in rows:
+            name = r[ik].split("(")[0].replace("fpnmt::", "").replace("void ", "").strip()
+            a = acc.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += float(r[it])
+            a[2] += float(r[ib]) * scale * float(r[it]) * 1e-6
+        json.dump({"source": "%s (ncu --set full, cold cache, --clock-control none) %s" % (rep, note),
+                   "kernels": {k: {"launches": a[0], "mean_ncu_us": a[1] / a[0], "mean_dram_bytes": a[2] / a[0]}
+                               for k, a in acc.items()}}, open(dst, "w"), indent=1)
+        print("wrote", dst, {k: a[0] for k, a in acc.items()})
     elif mode == "details":
         rep, dst = sys.argv[2:4]
         hdr, units, rows = raw(rep)
