@@ -107,6 +107,15 @@ FPNMT_API int fpnmt_generate(fpnmt_handle* h, const float* images, int on_host, 
   return h->eng->generate(images, on_host, out_ids, out_len, outputs_on_host, early_stop, step_scores,
                           (cudaStream_t)stream);
 }
+FPNMT_API int fpnmt_stage_images(fpnmt_handle* h, const float* host_images, int slot) {
+  CHECK_H(h);
+  return h->eng->stage_images(host_images, slot);
+}
+FPNMT_API int fpnmt_generate_staged(fpnmt_handle* h, int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host,
+                                    int early_stop, float* step_scores, void* stream) {
+  CHECK_H(h);
+  return h->eng->generate_staged(slot, out_ids, out_len, outputs_on_host, early_stop, step_scores, (cudaStream_t)stream);
+}
 FPNMT_API int fpnmt_decode(fpnmt_handle* h, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop,
                  float* step_scores, void* stream) {
   CHECK_H(h);

@@ -332,88 +332,130 @@ int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, 
 
 // ---------------------------------------------------------------------------------------- decoder attention
 // Warp-level attention of ONE query over Tk cached positions.  The query (pre-scaled) lives in shared memory
-// (broadcast reads).  Score pass: lane j owns position k0+j and reads its 128 B key row with 8 independent 16 B
-// loads (memory-level parallelism, few registers); value pass: lanes own 2 output dims and the probabilities are
-// broadcast by shuffle, loads unrolled.  `krow(pos)` maps a position to the row of the K/V views.
+// (broadcast reads).  `krow(pos)` maps a position to the row of the K/V views.
+// Value pass layout: lane = pg * 8 + dg owns output dims dg*8 .. dg*8+7 for the positions p = pg (mod 4).  The V rows of
+// the 32-position chunk are copied into per-warp shared memory with cp.async (16 B units, consecutive lanes = consecutive
+// units, so the global reads are 128 B row segments and the shared writes are conflict-free) WHILE the score pass still
+// reads the K rows into registers: the two dependent DRAM round trips of the chunk (K, then V) become one.  The
+// probabilities and cache rows of the chunk sit in per-warp shared arrays, and the four position groups are summed by
+// two xor-shuffles at the end.
 template <bool SPLIT>
-__device__ __forceinline__ float dot_row64(const Act& a, size_t row, int col, const float* __restrict__ qs) {
-  const bf16* p = a.p + row * (size_t)a.ld + col;
-  uint4 h[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const uint4*>(p + i * 8);
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float f[8];
-    unpack8(h[i], f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(qs[i * 8 + j], f[j], acc);
-  }
-  if constexpr (SPLIT) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const uint4*>(p + a.lo + i * 8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float f[8];
-      unpack8(h[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc = fmaf(qs[i * 8 + j], f[j], acc);
-    }
-  }
-  return acc;
-}
-
-// Value pass layout: lane = pg * 8 + dg owns output dims dg*8 .. dg*8+7 for the positions p = pg (mod 4); each lane issues
-// one 16-byte load per position (a warp covers 4 positions x 128 B per instruction), the probabilities and cache rows of
-// the 32-position chunk sit in per-warp shared arrays, and the four position groups are summed by two xor-shuffles at
-// the end.  (The previous layout walked the positions one by one with two shuffles and a 4-byte load per lane.)
-struct WarpScratch {
-  float q[DH];        // pre-scaled query
-  float p[32];        // probabilities of the current chunk
-  unsigned row[32];   // K/V rows of the current chunk
+struct __align__(16) WarpScratchT {
+  uint4 v[(SPLIT ? 2 : 1) * 32 * 8];   // V rows of the current chunk: [hi | lo][position][8 x 16 B]
+  float q[DH];                         // pre-scaled query
+  unsigned row[32];                    // K/V rows of the current chunk
 };
 
 template <bool SPLIT>
-__device__ __forceinline__ void pv_accumulate(const Act& vc, int v_col, const WarpScratch& ws, int kmax, int lane, float* o) {
-  const int pg = lane >> 3, dg = lane & 7;
-#pragma unroll 4
-  for (int pp = pg; pp < kmax; pp += 4) {
-    const float w = ws.p[pp];
-    const bf16* src = vc.p + (size_t)ws.row[pp] * vc.ld + v_col + dg * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(src), f);
+__device__ __forceinline__ void v_stage_async(const Act& vc, int v_col, WarpScratchT<SPLIT>& ws, int kmax, int lane) {
+  const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(ws.v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(w, f[i], o[i]);
-    if constexpr (SPLIT) {
-      unpack8(*reinterpret_cast<const uint4*>(src + vc.lo), f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(w, f[i], o[i]);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int u = i * 32 + lane, r = u >> 3;
+    const bool ok = r < kmax;
+    const bf16* src = vc.p + (size_t)ws.row[ok ? r : 0] * vc.ld + v_col + (u & 7) * 8;
+    cp16(dst0 + u * 16, src, ok);
+    if constexpr (SPLIT) cp16(dst0 + (256 + u) * 16, src + vc.lo, ok);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// Score and value pass share one mapping: lane = pg * 8 + dg handles the positions pp = pg (mod 4) of the chunk and the
+// dims dg*8 .. dg*8+7.  Per load instruction a warp therefore covers 4 positions x 128 contiguous bytes (4 L1 wavefronts;
+// the earlier "one key row per lane" layout touched 32 different lines per instruction and was bound by the L1 tag
+// stage), the 8-dim partial dot products are summed over the 8 dg lanes with three xor-shuffles, and the probabilities
+// stay in the registers of exactly the lanes that need them for the value pass.
 template <bool SPLIT, typename RowFn>
-__device__ __forceinline__ void warp_attend(WarpScratch& ws, const Act& kc, int k_col, const Act& vc, int v_col, int Tk,
+__device__ __forceinline__ void warp_attend(WarpScratchT<SPLIT>& ws, const Act& kc, int k_col, const Act& vc, int v_col, int Tk,
                                             RowFn krow, int lane, float& m, float& l, float* o) {
+  const int pg = lane >> 3, dg = lane & 7;
+  float q8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q8[j] = ws.q[dg * 8 + j];
   for (int k0 = 0; k0 < Tk; k0 += 32) {
     const int pos = k0 + lane;
-    float sc = -INFINITY;
-    unsigned myrow = 0;
-    if (pos < Tk) {
-      myrow = (unsigned)krow(pos);
-      sc = dot_row64<SPLIT>(kc, myrow, k_col, ws.q);
+    const int kmax = min(32, Tk - k0);
+    ws.row[lane] = (pos < Tk) ? (unsigned)krow(pos) : 0u;
+    __syncwarp();
+    v_stage_async<SPLIT>(vc, v_col, ws, kmax, lane);
+    float sc[8];
+    {
+      uint4 kh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pp = pg + 4 * i;
+        const bf16* src = kc.p + (size_t)ws.row[pp < kmax ? pp : 0] * kc.ld + k_col + dg * 8;
+        kh[i] = *reinterpret_cast<const uint4*>(src);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float f[8];
+        unpack8(kh[i], f);
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(q8[j], f[j], a);
+        sc[i] = a;
+      }
+      if constexpr (SPLIT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pp = pg + 4 * i;
+          const bf16* src = kc.p + (size_t)ws.row[pp < kmax ? pp : 0] * kc.ld + k_col + dg * 8 + kc.lo;
+          kh[i] = *reinterpret_cast<const uint4*>(src);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float f[8];
+          unpack8(kh[i], f);
+          float a = sc[i];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a = fmaf(q8[j], f[j], a);
+          sc[i] = a;
+        }
+      }
     }
-    const float mn = fmaxf(m, warp_max(sc));
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 1);
+      sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 2);
+      sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 4);
+      if (pg + 4 * i >= kmax) sc[i] = -INFINITY;
+      cmax = fmaxf(cmax, sc[i]);
+    }
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
+    const float mn = fmaxf(m, cmax);
     const float corr = __expf(m - mn);
-    const float p = (pos < Tk) ? __expf(sc - mn) : 0.f;
-    l = l * corr + warp_sum(p);
+    float psum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = (pg + 4 * i < kmax) ? __expf(sc[i] - mn) : 0.f;      // sc[] now holds the probabilities
+      psum += sc[i];
+    }
+    psum += __shfl_xor_sync(0xffffffffu, psum, 8);
+    psum += __shfl_xor_sync(0xffffffffu, psum, 16);
+    l = l * corr + psum;
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] *= corr;
     m = mn;
-    ws.p[lane] = p;
-    ws.row[lane] = myrow;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    pv_accumulate<SPLIT>(vc, v_col, ws, min(32, Tk - k0), lane, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pp = pg + 4 * i;
+      if (pp < kmax) {
+        float f[8];
+        unpack8(ws.v[pp * 8 + dg], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[i], f[j], o[j]);
+        if constexpr (SPLIT) {
+          unpack8(ws.v[256 + pp * 8 + dg], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[i], f[j], o[j]);
+        }
+      }
+    }
     __syncwarp();
   }
 }
@@ -436,17 +478,29 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
                                                                        const int* __restrict__ anc_base, size_t anc_stride,
                                                                        const int* __restrict__ step, int rows, int T,
                                                                        int heads, Act out) {
-  __shared__ WarpScratch s_ws[DEC_WARPS];
+  __shared__ WarpScratchT<SPLIT> s_ws[DEC_WARPS];
   pdl_launch();
   pdl_wait();
   const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  WarpScratch& ws = s_ws[w];
+  WarpScratchT<SPLIT>& ws = s_ws[w];
   const int row = gw / heads, h = gw % heads;
   const int d = heads * DH;
+  // The ancestry entries of the first 64 positions are fetched for BOTH parities of the double-buffered table together
+  // with the step counter, so the address of the K/V rows is one memory round trip away instead of two.
+  const int* anc_e = anc_base + (size_t)row * T;
+  const int* anc_o = anc_e + anc_stride;
+  int a_e[2], a_o[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int pos = c * 32 + lane;
+    a_e[c] = pos < T ? __ldg(anc_e + pos) : 0;
+    a_o[c] = pos < T ? __ldg(anc_o + pos) : 0;
+  }
   const int t = *step;
-  const int* anc = anc_base + (size_t)(t & 1) * anc_stride + (size_t)row * T;
+  const int* anc = (t & 1) ? anc_o : anc_e;
+  const int a0 = (t & 1) ? a_o[0] : a_e[0], a1 = (t & 1) ? a_o[1] : a_e[1];
   const float2 qv = ld_pair(qkv, row, h * DH, lane);
   const float2 kn = ld_pair(qkv, row, d + h * DH, lane);
   const float2 vn = ld_pair(qkv, row, 2 * d + h * DH, lane);
@@ -458,7 +512,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
-  warp_attend<SPLIT>(ws, kc, h * DH, vc, h * DH, t, [&](int pos) { return (size_t)anc[pos] * T + pos; }, lane, m, l, o);
+  warp_attend<SPLIT>(ws, kc, h * DH, vc, h * DH, t,
+                     [&](int pos) { return (size_t)(pos < 32 ? a0 : pos < 64 ? a1 : anc[pos]) * T + pos; }, lane, m, l, o);
   pv_reduce(o);
   {   // the new position itself (K/V still in registers): fold it in on lanes 0..7
     const float sc = warp_sum((qv.x * kn.x + qv.y * kn.y) * 0.125f);
@@ -498,13 +553,13 @@ int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, c
 template <bool SPLIT>
 __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows,
                                                                         int beam, int Tk, int heads, Act out) {
-  __shared__ WarpScratch s_ws[DEC_WARPS];
+  __shared__ WarpScratchT<SPLIT> s_ws[DEC_WARPS];
   pdl_launch();
   pdl_wait();
   const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  WarpScratch& ws = s_ws[w];
+  WarpScratchT<SPLIT>& ws = s_ws[w];
   const int row = gw / heads, h = gw % heads;
   const int img = row / beam;
   const float2 qv = ld_pair(q, row, h * DH, lane);

@@ -106,24 +106,37 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
   }
   const float tmax_v = m;                                  // this thread's largest logit
-  // ---- row max and sum of exponentials
-  m = warp_max(m);
-  if (lane == 0) s_m[warp] = m;
-  __syncthreads();
-#pragma unroll
-  for (int w = 0; w < NW; ++w) m = fmaxf(m, s_m[w]);
+  // ---- row max and sum of exponentials, ONE block barrier: every thread sums its own slots relative to its own
+  // maximum (it only re-reads what it wrote itself), warps and then the block combine (max, rescaled sum) pairs.
   float sum = 0.f;
+  if (tmax_v > -INFINITY) {
 #pragma unroll 4
-  for (int i = 0; i < nv4; ++i) {
-    const float4 q = s_row4[i * THREADS + tid];
-    sum += expf(q.x - m) + expf(q.y - m) + expf(q.z - m) + expf(q.w - m);   // exp(-inf) = 0 for the padding
+    for (int i = 0; i < nv4; ++i) {
+      const float4 q = s_row4[i * THREADS + tid];
+      sum += expf(q.x - tmax_v) + expf(q.y - tmax_v) + expf(q.z - tmax_v) + expf(q.w - tmax_v);   // exp(-inf) = 0: padding
+    }
   }
-  sum = warp_sum(sum);
-  if (lane == 0) s_s[warp] = sum;
+  {
+    const float wm = warp_max(tmax_v);
+    sum = warp_sum(tmax_v > -INFINITY ? sum * expf(tmax_v - wm) : 0.f);
+    if (lane == 0) {
+      s_m[warp] = wm;
+      s_s[warp] = sum;
+    }
+    s_cv[warp * 32 + lane] = tmax_v;                        // thread maxima, for the selection threshold below
+  }
+  constexpr int CAP = 128;
+  __shared__ float s_lv[CAP];
+  __shared__ int s_li[CAP];
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
   __syncthreads();
+  m = s_m[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) m = fmaxf(m, s_m[w]);
   sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < NW; ++w) sum += s_s[w];
+  for (int w = 0; w < NW; ++w) sum += s_s[w] * expf(s_m[w] - m);
   // ---- candidate score of a logit (pipeline.py:117,122 in prob mode; the same ordering in the log domain otherwise).
   // Every step of it is monotone non-decreasing in floating point, so max_e cand(v_e) == cand(max_e v_e) exactly.
   const float lse = m + logf(sum);
@@ -131,52 +144,27 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   auto cand = [&](float vv) -> float { return prob ? (expf(vv - m) / sum) * score : score + (vv - lse); };
 
   // ---- row-local top-N (tf.math.top_k order: value descending, lower index first).
-  // Fast path: tau = N-th largest of the per-thread maxima is a lower bound of the N-th largest candidate, so every
-  // winner satisfies c >= tau; those few elements (typically N..2N of V) are gathered into a shared list and warp 0
-  // selects among them.  If more than CAP elements reach tau (massive ties, e.g. the reference's probability
-  // underflow regime where every candidate is 0), the exact but slower rescan path below takes over.
-  constexpr int CAP = 128;
-  __shared__ float s_lv[CAP];
-  __shared__ int s_li[CAP];
-  __shared__ float s_tau;
-  __shared__ int s_cnt;
-  if (tid == 0) s_cnt = 0;
+  // Fast path: the 32 "lane groups" (threads with the same lane id, one per warp) hold 32 disjoint parts of the row; the
+  // N-th largest of their maxima, tau, is a lower bound of the N-th largest candidate (N distinct elements reach it), so
+  // every winner satisfies c >= tau.  Those few elements (typically N..2N of V) are gathered into a shared list and
+  // ranked by counting (rank = number of better entries; no serial arg-max rounds).  If more than CAP elements reach tau
+  // (massive ties, e.g. the reference's probability underflow regime where every candidate is 0), the exact but slower
+  // rescan path below takes over.  Every warp derives tau redundantly from the shared maxima: no extra barrier.
+  float tau;
   {
-    float tm = cand(tmax_v);
-    for (int k = 0; k < N; ++k) {                           // per warp: its N largest thread maxima (values only)
-      const float w = warp_max(tm);
-      if (lane == 0) s_cv[warp * 32 + k] = w;
-      const unsigned hit = __ballot_sync(0xffffffffu, tm == w);
-      if (lane == __ffs(hit) - 1) tm = -INFINITY;
+    float g = s_cv[lane];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) g = fmaxf(g, s_cv[w * 32 + lane]);
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float gj = __shfl_sync(0xffffffffu, g, j);
+      rank += (gj > g || (gj == g && j < lane)) ? 1 : 0;
     }
+    const unsigned hit = __ballot_sync(0xffffffffu, rank == N - 1);      // ranks are a permutation of 0..31
+    tau = cand(__shfl_sync(0xffffffffu, g, __ffs(hit) - 1));
   }
-  __syncthreads();
-  if (warp == 0) {
-    float cv[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) cv[w] = lane < N ? s_cv[w * 32 + lane] : -INFINITY;
-    float tau = -INFINITY;
-    for (int k = 0; k < N; ++k) {
-      float b2 = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) b2 = fmaxf(b2, cv[w]);
-      tau = warp_max(b2);
-      const unsigned hit = __ballot_sync(0xffffffffu, b2 == tau);
-      if (lane == __ffs(hit) - 1) {                         // drop ONE instance of the maximum
-        bool dropped = false;
-#pragma unroll
-        for (int w = 0; w < NW; ++w)
-          if (!dropped && cv[w] == tau) {
-            cv[w] = -INFINITY;
-            dropped = true;
-          }
-      }
-    }
-    if (lane == 0) s_tau = tau;
-  }
-  __syncthreads();
   {
-    const float tau = s_tau;
 #pragma unroll 2
     for (int i = 0; i < nv4; ++i) {
       const float4 q = s_row4[i * THREADS + tid];
@@ -197,32 +185,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   __syncthreads();
   const int cnt = s_cnt;
   if (cnt <= CAP && cnt >= N) {
-    if (warp == 0) {
-      float cv[CAP / 32];
-      int ci[CAP / 32];
-#pragma unroll
-      for (int q = 0; q < CAP / 32; ++q) {
-        const int idx = lane + 32 * q;
-        cv[q] = idx < cnt ? s_lv[idx] : -INFINITY;
-        ci[q] = idx < cnt ? s_li[idx] : 0x7fffffff;
-      }
-      for (int k = 0; k < N; ++k) {
-        float b2 = -INFINITY;
-        int i2 = 0x7fffffff;
-#pragma unroll
-        for (int q = 0; q < CAP / 32; ++q)
-          if (ci[q] != 0x7fffffff && better(cv[q], ci[q], b2, i2)) {
-            b2 = cv[q];
-            i2 = ci[q];
-          }
-        warp_argmax(b2, i2);
-#pragma unroll
-        for (int q = 0; q < CAP / 32; ++q)
-          if (ci[q] == i2) ci[q] = 0x7fffffff;
-        if (lane == 0) {
-          st.cand_val[(size_t)row * N + k] = b2;
-          st.cand_idx[(size_t)row * N + k] = i2;
-        }
+    if (tid < cnt) {
+      const float v = s_lv[tid];
+      const int e = s_li[tid];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += better(s_lv[j], s_li[j], v, e) ? 1 : 0;
+      if (rank < N) {
+        st.cand_val[(size_t)row * N + rank] = v;
+        st.cand_idx[(size_t)row * N + rank] = e;
+        __threadfence();                                    // visible before the image counter moves
       }
     }
   } else {
@@ -304,12 +275,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       }
     }
   }
-  if (warp == 0) {
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence();                                      // candidates visible before the image counter moves
-      s_last = (atomicAdd(st.img_count + row / N, 1) == N - 1);
-    }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();                                        // candidates visible before the image counter moves
+    s_last = (atomicAdd(st.img_count + row / N, 1) == N - 1);
   }
   __syncthreads();
   if (!s_last) return;
@@ -320,58 +289,38 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   const int cur = t & 1, nxt = cur ^ 1;
   const int NN = N * N;
   const int rows0 = b * N;
-  if (warp == 0) {
-    st.img_count[b] = 0;                                    // re-armed for the next step
-    float cv[32];
-    int cf[32];
-#pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      const int c = lane + 32 * s;
-      cv[s] = -INFINITY;
-      cf[s] = 0x7fffffff;
-      if (c < NN) {
-        const int tok = __ldcg(st.cand_idx + (size_t)rows0 * N + c);
-        if (tok != 0x7fffffff) {
-          cv[s] = __ldcg(st.cand_val + (size_t)rows0 * N + c);
-          cf[s] = (c / N) * V + tok;                               // flat index over the N x V candidates
-        }
-      }
-      if (32 * (s + 1) >= NN) break;
+  // N x N candidates of the image, ranked by counting over the flat index order (pipeline.py:127-131)
+  float* s_fv = reinterpret_cast<float*>(s_row4);           // [N*N] values   (the row staging area is free now;
+  int* s_ff = reinterpret_cast<int*>(s_fv + 1024);          // [N*N] flat ids  the launcher sizes it >= 8 KB)
+  if (tid < 32) {
+    s_parent[tid] = 0;
+    s_token[tid] = 0;
+  }
+  if (tid == 0) st.img_count[b] = 0;                        // re-armed for the next step
+  for (int c = tid; c < NN; c += THREADS) {
+    const int tok = __ldcg(st.cand_idx + (size_t)rows0 * N + c);
+    const bool ok = tok != 0x7fffffff;
+    s_fv[c] = ok ? __ldcg(st.cand_val + (size_t)rows0 * N + c) : -INFINITY;
+    s_ff[c] = ok ? (c / N) * V + tok : 0x7fffffff;          // flat index over the N x V candidates
+  }
+  __syncthreads();
+  for (int c = tid; c < NN; c += THREADS) {
+    const int f = s_ff[c];
+    if (f == 0x7fffffff) continue;
+    const float v = s_fv[c];
+    int rank = 0;
+    for (int j = 0; j < NN; ++j) rank += better(s_fv[j], s_ff[j], v, f) ? 1 : 0;
+    if (rank < N) {                                         // new beam `rank` (scores sorted, ties -> lower flat index)
+      const int par = f / V;                                // pipeline.py:130
+      const int tok = f - par * V;                          // pipeline.py:131
+      s_parent[rank] = par;
+      s_token[rank] = tok;
+      st.score[nxt][rows0 + rank] = v;
+      st.last_tok[rows0 + rank] = tok;
+      if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + rank] = par;
+      if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + rank] = tok;
+      if (rank == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = v;
     }
-    int my_parent = 0, my_token = 0;
-    float my_score = 0.f;
-    for (int k = 0; k < N; ++k) {
-      float b2 = -INFINITY;
-      int i2 = 0x7fffffff;
-#pragma unroll
-      for (int s = 0; s < 32; ++s) {
-        if (cf[s] != 0x7fffffff && better(cv[s], cf[s], b2, i2)) {
-          b2 = cv[s];
-          i2 = cf[s];
-        }
-        if (32 * (s + 1) >= NN) break;
-      }
-      warp_argmax(b2, i2);
-#pragma unroll
-      for (int s = 0; s < 32; ++s) {
-        if (cf[s] == i2) cf[s] = 0x7fffffff;
-        if (32 * (s + 1) >= NN) break;
-      }
-      if (lane == k) {
-        my_parent = i2 / V;                                          // pipeline.py:130
-        my_token = i2 - my_parent * V;                               // pipeline.py:131
-        my_score = b2;
-      }
-    }
-    if (lane < N) {                                                  // lanes 0..N-1 hold the new beams in rank order
-      s_parent[lane] = my_parent;
-      s_token[lane] = my_token;
-      st.score[nxt][rows0 + lane] = my_score;
-      st.last_tok[rows0 + lane] = my_token;
-      if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + lane] = my_parent;
-      if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + lane] = my_token;
-    }
-    if (lane == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = my_score;
   }
   __syncthreads();
   for (int n = warp; n < N; n += NW) {
@@ -433,7 +382,8 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
   }
   const int threads = st.V <= 16384 ? 256 : 512;
   const int nv4 = (st.V + 4 * threads - 1) / (4 * threads);
-  const size_t smem = (size_t)nv4 * threads * 16;
+  size_t smem = (size_t)nv4 * threads * 16;
+  if (smem < 8192) smem = 8192;                             // phase 2 keeps the N x N merge list there
   if (nv4 > 32 || smem > 200 * 1024) {
     set_last_error("beam_step: vocabulary too large (max 65536)");
     return 1;

@@ -44,6 +44,14 @@ Engine::~Engine() {
   if (step_graph_) cudaGraphExecDestroy(step_graph_);
   if (loop_graph_) cudaGraphExecDestroy(loop_graph_);
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  if (copy_stream_) {
+    cudaStreamSynchronize(copy_stream_);
+    cudaStreamDestroy(copy_stream_);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (stage_ready_[i]) cudaEventDestroy(stage_ready_[i]);
+    if (stage_free_[i]) cudaEventDestroy(stage_free_[i]);
+  }
   if (h_pinned_) cudaFreeHost(h_pinned_);
   for (void* p : allocs_) cudaFree(p);
 }
@@ -1140,6 +1148,39 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
 int Engine::generate(const float* images, int on_host, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop,
                      float* step_scores, cudaStream_t s) {
   RC(encode(images, on_host, nullptr, s, false));
+  return decode(out_ids, out_len, out_on_host, early_stop, step_scores, s);
+}
+
+// Double-buffered input (the role of dataset.py:90-92's map/prefetch in the reference's input pipeline): the copy of the
+// next batch runs on the engine's own stream, ordered against the compute stream with two events per slot.
+int Engine::stage_images(const float* host_images, int slot) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "stage_images before finalize_weights");
+  if (!host_images || slot < 0 || slot > 1) return fail(FPNMT_ERR_INVALID, "stage_images: NULL images or slot not 0/1");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  const size_t n = (size_t)cfg_.batch * cfg_.image_size * cfg_.image_size * 3;
+  if (!copy_stream_) FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  if (!stage_buf_[slot]) {
+    stage_buf_[slot] = (float*)dalloc(n * 4);
+    if (!stage_buf_[slot]) return FPNMT_ERR_CUDA;
+    FPNMT_CUDA_OK(cudaEventCreateWithFlags(&stage_ready_[slot], cudaEventDisableTiming));
+    FPNMT_CUDA_OK(cudaEventCreateWithFlags(&stage_free_[slot], cudaEventDisableTiming));
+  } else {
+    FPNMT_CUDA_OK(cudaStreamWaitEvent(copy_stream_, stage_free_[slot], 0));   // last consumer of this slot is done
+  }
+  FPNMT_CUDA_OK(cudaMemcpyAsync(stage_buf_[slot], host_images, n * 4, cudaMemcpyHostToDevice, copy_stream_));
+  FPNMT_CUDA_OK(cudaEventRecord(stage_ready_[slot], copy_stream_));
+  stage_filled_[slot] = true;
+  return 0;
+}
+
+int Engine::generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop, float* step_scores,
+                            cudaStream_t s) {
+  if (slot < 0 || slot > 1 || !stage_filled_[slot]) return fail(FPNMT_ERR_STATE, "generate_staged: slot was not staged");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  FPNMT_CUDA_OK(cudaStreamWaitEvent(s, stage_ready_[slot], 0));
+  RC(encode(stage_buf_[slot], 0, nullptr, s, false));
+  FPNMT_CUDA_OK(cudaEventRecord(stage_free_[slot], s));
+  stage_filled_[slot] = false;
   return decode(out_ids, out_len, out_on_host, early_stop, step_scores, s);
 }
 

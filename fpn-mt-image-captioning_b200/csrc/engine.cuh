@@ -59,6 +59,10 @@ class Engine {
   int generate(const float* images, int on_host, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop,
                float* step_scores, cudaStream_t s);
   int profile(int iters, char* buf, size_t cap);
+  // double-buffered host input: copy batch i+1 on the engine's copy stream while batch i runs
+  int stage_images(const float* host_images, int slot);
+  int generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop, float* step_scores,
+                      cudaStream_t s);
   int64_t launches = 0;
 
  private:
@@ -81,6 +85,11 @@ class Engine {
   // buffers referenced at run time
   const float** img_slot_ = nullptr;      // device slot holding the current image pointer
   float* img_stage_ = nullptr;            // device staging for host images
+  float* stage_buf_[2] = {nullptr, nullptr};          // fpnmt_stage_images slots
+  cudaEvent_t stage_ready_[2] = {nullptr, nullptr};   // copy of the slot finished (recorded on copy_stream_)
+  cudaEvent_t stage_free_[2] = {nullptr, nullptr};    // encoder has consumed the slot (recorded on the compute stream)
+  bool stage_filled_[2] = {false, false};
+  cudaStream_t copy_stream_ = nullptr;
   Tensor feat_[5];                        // head outputs P3..P7
   Tensor enc_out_;                        // (B*16, 512)
   int n_base_ = 16;                       // tokens of the baseline view

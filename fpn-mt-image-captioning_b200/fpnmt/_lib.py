@@ -44,6 +44,8 @@ SIGNATURES = {
     "fpnmt_decode_logits": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "fpnmt_beam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fpnmt_generate": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "fpnmt_stage_images": (_i, [_vp, _vp, _i]),
+    "fpnmt_generate_staged": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "fpnmt_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "fpnmt_profile": (_i, [_vp, _i, C.c_char_p, C.c_size_t]),
     "fpnmt_launch_count": (C.c_int64, [_vp]),

@@ -164,6 +164,50 @@ class Engine:
                                            _stream_ptr(self.device)))
         return (ids, lens, scores) if return_scores else (ids, lens)
 
+    def stage(self, host_images, slot: int):
+        """Enqueue the host->device copy of one batch into staging slot 0/1 on the engine's copy stream (returns at once).
+        Returns the host tensor actually handed to the copy; keep it alive until the matching generate_staged is done."""
+        t = torch.as_tensor(host_images)
+        if t.device.type != "cpu":
+            raise ValueError("stage() takes HOST images; device images go straight to generate()")
+        s = self.image_size
+        if tuple(t.shape) != (self.batch, s, s, 3):
+            raise ValueError("images must be NHWC (%d,%d,%d,3), got %s" % (self.batch, s, s, tuple(t.shape)))
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        _lib.check(self.lib.fpnmt_stage_images(self._h, t.data_ptr(), int(slot)))
+        return t
+
+    def generate_staged(self, slot: int, early_stop: bool = True, to_host: bool = True):
+        """`generate` on a batch previously handed to `stage(…, slot)`."""
+        if to_host:
+            ids = torch.empty((self.batch, self.max_len), dtype=torch.int32).pin_memory()
+            lens = torch.empty((self.batch,), dtype=torch.int32).pin_memory()
+        else:
+            ids = torch.empty((self.batch, self.max_len), dtype=torch.int32, device=self.device)
+            lens = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.fpnmt_generate_staged(self._h, int(slot), ids.data_ptr(), lens.data_ptr(), int(to_host),
+                                                  int(early_stop), None, _stream_ptr(self.device)))
+        return ids, lens
+
+    def generate_stream(self, batches, early_stop: bool = True):
+        """Captions for an iterable of HOST batches with the copy of batch i+1 overlapped with the compute of batch i
+        (the tf.data prefetch of dataset.py:92).  Yields (ids, lens) host tensors per batch, in order."""
+        it = iter(batches)
+        try:
+            keep = [self.stage(next(it), 0), None]
+        except StopIteration:
+            return
+        i = 0
+        while True:
+            nxt = next(it, None)
+            if nxt is not None:
+                keep[(i + 1) & 1] = self.stage(nxt, (i + 1) & 1)
+            yield self.generate_staged(i & 1, early_stop=early_stop, to_host=True)
+            if nxt is None:
+                return
+            i += 1
+
     def decode(self, early_stop: bool = True, to_host: bool = True):
         """Decode half only, from the memory left by the last `encode`."""
         if to_host:

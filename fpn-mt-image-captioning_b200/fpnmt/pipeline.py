@@ -71,26 +71,40 @@ class Pipeline:
 
     def evaluate(self, generator: Iterable, max_seq_len, batch_size: int = 1) -> List[dict]:
         """pipeline.py:156-175: [(img, imgId)] -> [{"image_id", "caption"}] (optionally batched)."""
-        results, buf = [], []
+        # Batches are packed into two alternating pinned buffers and streamed through Engine.generate_stream, so the
+        # host->device copy of batch i+1 overlaps the compute of batch i (dataset.py:90-92's prefetch).
+        eng = self.transformer.engine(int(batch_size), self.beam, max_seq_len or self.max_seq_len)
+        s = eng.image_size
+        pinned = [None, None]
+        metas: List[list] = []
 
-        def flush():
-            if not buf:
-                return
-            imgs = torch.stack([torch.as_tensor(i) for i, _ in buf])
-            n = len(buf)
-            if n < batch_size:                                   # pad the last batch
-                imgs = torch.cat([imgs, imgs[-1:].expand(batch_size - n, -1, -1, -1)])
-            ids, lens = self.predict_batch(imgs, max_seq_len)
-            for j in range(n):
+        def pack(buf, k):
+            if pinned[k & 1] is None:
+                pinned[k & 1] = torch.empty((batch_size, s, s, 3), dtype=torch.float32).pin_memory()
+            dst = pinned[k & 1]
+            for j, (img, _) in enumerate(buf):
+                dst[j].copy_(torch.as_tensor(img))
+            for j in range(len(buf), batch_size):                # pad the last batch
+                dst[j].copy_(dst[len(buf) - 1])
+            metas.append([m for _, m in buf])
+            return dst
+
+        def batches():
+            buf, k = [], 0
+            for item in generator:
+                buf.append(item)
+                if len(buf) == batch_size:
+                    yield pack(buf, k)
+                    buf, k = [], k + 1
+            if buf:
+                yield pack(buf, k)
+
+        results = []
+        for i, (ids, lens) in enumerate(eng.generate_stream(batches(), early_stop=True)):
+            ids, lens = ids.numpy(), lens.numpy()
+            for j, image_id in enumerate(metas[i]):
                 text = self.tokenizer.sequences_to_texts([ids[j, :lens[j]]])[0]          # pipeline.py:169
-                results.append({"image_id": buf[j][1], "caption": text})
-            buf.clear()
-
-        for item in generator:
-            buf.append(item)
-            if len(buf) == batch_size:
-                flush()
-        flush()
+                results.append({"image_id": image_id, "caption": text})
         return results
 
     def evaluate_img(self, img, max_seq_len) -> List[dict]:

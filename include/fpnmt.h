@@ -119,6 +119,16 @@ FPNMT_API int fpnmt_beam_step(fpnmt_handle* h, const float* logits, const float*
  * step_scores: optional DEVICE float32 [max_len, batch] score of the top beam after each step (may be NULL). */
 FPNMT_API int fpnmt_generate(fpnmt_handle* h, const float* images, int images_on_host, int32_t* out_ids, int32_t* out_len,
                    int outputs_on_host, int early_stop, float* step_scores, void* stream);
+/* Replaces: the input overlap the reference gets from tf.data (dataset.py:90-92, map(load_image, AUTOTUNE) +
+ * prefetch(AUTOTUNE)): double-buffered HOST input.  fpnmt_stage_images enqueues the host->device copy of a whole batch
+ * (HOST float32 [batch, S, S, 3]; pinned memory for a truly asynchronous copy) into staging slot 0 or 1 on the engine's
+ * own copy stream and returns at once; the buffer must stay valid until the matching fpnmt_generate_staged has been
+ * issued and its stream synchronised.  fpnmt_generate_staged is fpnmt_generate on a staged slot: `stream` waits for that
+ * slot's copy, runs encoder + decode, and releases the slot as soon as the encoder has consumed it.  Typical loop:
+ * stage(0); for i: stage((i+1)&1, batch i+1); generate_staged(i&1, ...).  Error: FPNMT_ERR_STATE if the slot is empty. */
+FPNMT_API int fpnmt_stage_images(fpnmt_handle* h, const float* host_images, int slot);
+FPNMT_API int fpnmt_generate_staged(fpnmt_handle* h, int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host,
+                                    int early_stop, float* step_scores, void* stream);
 /* Same, from an encoder output already in the engine (after fpnmt_encode) — the decode half only. */
 FPNMT_API int fpnmt_decode(fpnmt_handle* h, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop,
                  float* step_scores, void* stream);

@@ -328,3 +328,28 @@ def test_engine_error_paths():
         Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=64, vocab=V, max_len=T, num_layers=L, image_size=256)
     with pytest.raises(FpnmtError):
         Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=300)
+
+
+def test_double_buffered_host_input_matches_one_shot_generate():
+    """fpnmt_stage_images + fpnmt_generate_staged (Engine.generate_stream): same captions as the one-shot call for
+    every batch of a stream, in order, including a stream of one batch; an empty slot is a state error."""
+    from fpnmt._lib import FpnmtError
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=4)
+    eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16x3")
+    batches = [O.test_images(B, S, seed=30 + i).pin_memory() for i in range(5)]
+    want = [eng.generate(b, early_stop=False) for b in batches]
+    got = list(eng.generate_stream(iter(batches), early_stop=False))
+    assert len(got) == 5
+    for (i0, l0), (i1, l1) in zip(want, got):
+        assert torch.equal(i0, i1) and torch.equal(l0, l1)
+    one = list(eng.generate_stream([batches[2].numpy()], early_stop=True))       # pageable numpy input, early stop
+    ref_ids, ref_len = eng.generate(batches[2], early_stop=True)
+    assert len(one) == 1 and torch.equal(one[0][0], ref_ids) and torch.equal(one[0][1], ref_len)
+    assert list(eng.generate_stream([], early_stop=True)) == []
+    with pytest.raises(FpnmtError):
+        eng.generate_staged(1)
+    with pytest.raises(ValueError):
+        eng.stage(torch.zeros(B, S, S, 3).cuda(), 0)
+    eng.close()
