@@ -282,8 +282,12 @@ def run_own(args, wl):
     if args.profile_out:
         with open(args.profile_out, "w") as f:
             json.dump(prof, f, indent=1)
-    enc_ops, step_ops = prof["encode"], prof["decode_step"]
-    T_steps = T
+    # with decoder groups the timed decode runs `decode_groups` concurrent chains over slices of the batch: the launches
+    # of one step are those of ONE group's chain (timed alone) times the number of groups
+    n_groups = int(prof.get("decode_groups", 1))
+    enc_ops = prof["encode"]
+    step_ops = prof["decode_group_step"] if n_groups > 1 else prof["decode_step"]
+    T_steps = T * n_groups
     # ---- per kernel family: launches per step, device time per step, algorithmic FLOPs / bytes per step
     fam = {}
 
@@ -331,7 +335,8 @@ def run_own(args, wl):
         tg = [v for k, v in ks.items() if k.startswith("tgemm_kernel")]
         if tg:
             traffic = sum(v["mean_dram_bytes"] * v["launches"] for v in tg) / sum(v["launches"] for v in tg)
-            traffic_src = "profiles/r01_ncu_traffic_decode_step.json (ncu --set full, mean over 11 tgemm launches, cold cache)"
+            traffic_src = ("profiles/r01_ncu_traffic_decode_step.json (ncu --set full, mean over %d tgemm launches, cold cache)"
+                           % sum(v["launches"] for v in tg))
     elif dom == "igemm" and "r01_ncu_traffic_igemm_encode.json" in traffic_tables and wl["backbone"] == "resnet50":
         ops_t = traffic_tables["r01_ncu_traffic_igemm_encode.json"]["ops"]
         traffic = sum(v["dram_bytes"] for v in ops_t.values()) / len(ops_t)
@@ -362,7 +367,7 @@ def run_own(args, wl):
                        "max_len": T, "image": "512x512x3 f32 NHWC", "weights": "random init (Keras default distributions)",
                        "l2": "per-step inputs (%.0f MB) and activations (GBs) exceed the 126 MB L2; two input batches alternate"
                              % (B * 512 * 512 * 3 * 4 / 1e6),
-                       "cuda_graphs": not args.no_graphs, "parallelism": "dp%d (image-sharded, ids all-gather)" % world},
+                       "cuda_graphs": not args.no_graphs, "decoder_groups": n_groups, "parallelism": "dp%d (image-sharded, ids all-gather)" % world},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 512 * 512 * 3 * 4,
                     "d2h_bytes_per_step": B * T * 4 + B * 4, "ms_per_step": ms_e2e / args.steps,
                     "api": "Engine.generate_stream (fpnmt_stage_images + fpnmt_generate_staged; double-buffered input)",

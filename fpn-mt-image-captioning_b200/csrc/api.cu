@@ -18,6 +18,13 @@ bool pdl_enabled() {
   }();
   return on;
 }
+bool pdl_small_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FPNMT_PDL");
+    return !(e && (e[0] == '0' || e[0] == '2'));
+  }();
+  return on;
+}
 }  // namespace fpnmt
 
 using namespace fpnmt;

@@ -538,15 +538,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
     st_act8(out, (size_t)row, h * DH + lane * 8, o);
   }
 }
-int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, const int* step, int rows, int T,
-                              int heads, Act out, cudaStream_t s) {
+int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, size_t anc_stride, const int* step, int rows,
+                              int T, int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
   if (kcache.lo)
-    FPNMT_CUDA_OK(launch_k(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                           qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
+    FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           qkv, kcache, vcache, anc, anc_stride, step, rows, T, heads, out));
   else
-    FPNMT_CUDA_OK(launch_k(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                           qkv, kcache, vcache, anc, (size_t)rows * T, step, rows, T, heads, out));
+    FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           qkv, kcache, vcache, anc, anc_stride, step, rows, T, heads, out));
   return 0;
 }
 

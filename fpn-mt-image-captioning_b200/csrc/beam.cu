@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       s_token[rank] = tok;
       st.score[nxt][rows0 + rank] = v;
       st.last_tok[rows0 + rank] = tok;
-      if (st.parent_out) st.parent_out[(size_t)t * st.B * N + rows0 + rank] = par;
-      if (st.token_out) st.token_out[(size_t)t * st.B * N + rows0 + rank] = tok;
-      if (rank == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.B + b] = v;
+      if (st.parent_out) st.parent_out[(size_t)t * st.Btot * N + rows0 + rank] = par;
+      if (st.token_out) st.token_out[(size_t)t * st.Btot * N + rows0 + rank] = tok;
+      if (rank == 0 && st.step_logprob) st.step_logprob[(size_t)t * st.Btot + b] = v;
     }
   }
   __syncthreads();
@@ -395,9 +395,9 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
     attr_done = true;
   }
   if (threads == 256)
-    FPNMT_CUDA_OK(launch_k(k_beam_step<256>, dim3(st.B * st.N), dim3(256), smem, s, st, logits, ld, em));
+    FPNMT_CUDA_OK(launch_k_small(k_beam_step<256>, dim3(st.B * st.N), dim3(256), smem, s, st, logits, ld, em));
   else
-    FPNMT_CUDA_OK(launch_k(k_beam_step<512>, dim3(st.B * st.N), dim3(512), smem, s, st, logits, ld, em));
+    FPNMT_CUDA_OK(launch_k_small(k_beam_step<512>, dim3(st.B * st.N), dim3(512), smem, s, st, logits, ld, em));
   return 0;
 }
 

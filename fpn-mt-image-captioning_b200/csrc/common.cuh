@@ -108,11 +108,13 @@ __device__ __forceinline__ void st_act8(const Act& a, size_t pix, int c, const f
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-bool pdl_enabled();   // FPNMT_PDL=0 disables the launch attribute (api.cu)
+bool pdl_enabled();         // FPNMT_PDL=0 disables the launch attribute (api.cu)
+bool pdl_small_enabled();   // FPNMT_PDL=2: only the tcgen05 GEMM kernels launch early; the small-footprint kernels of the
+                            // decode step (attention, beam) start after their predecessor has finished
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                            Args... args) {
+inline cudaError_t launch_k_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -122,8 +124,18 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  return launch_k_pdl(pdl_enabled(), kernel, grid, block, smem, stream, args...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args... args) {
+  return launch_k_pdl(pdl_small_enabled(), kernel, grid, block, smem, stream, args...);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "tensormap.cuh"
 #include "tgemm.cuh"
+#include "stem.cuh"
 #include "xattn.cuh"
 
 namespace fpnmt {
@@ -42,6 +43,12 @@ struct Op {
 };
 typedef std::vector<Op> Program;
 
+struct DecGroup {        // one independent decode chain over the images [b0, b0 + Bg) of the batch
+  int b0 = 0, Bg = 0;
+  BeamState bs{};
+  Program embed, step;
+};
+
 class Engine {
  public:
   Engine(const fpnmt_config& cfg, int device);
@@ -59,6 +66,8 @@ class Engine {
   int generate(const float* images, int on_host, int32_t* out_ids, int32_t* out_len, int out_on_host, int early_stop,
                float* step_scores, cudaStream_t s);
   int profile(int iters, char* buf, size_t cap);
+  int capture_groups(int T);
+  int add_stem(Program& p, const std::string& name, int kh, int pad, int cout, const GemmW& gw, int Kp, int act, const Tensor& out);
   // double-buffered host input: copy batch i+1 on the engine's copy stream while batch i runs
   int stage_images(const float* host_images, int slot);
   int generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop, float* step_scores,
@@ -80,6 +89,10 @@ class Engine {
   Program cnn_prog_, enc_prog_, dec_init_prog_, embed_prog_, step_prog_, step_forced_prog_;
   BeamEmbed beam_embed_{};
   cudaGraphExec_t cnn_graph_ = nullptr, enc_graph_ = nullptr, step_graph_ = nullptr, loop_graph_ = nullptr;
+  std::vector<DecGroup> groups_;          // decoder groups (empty: the whole batch is one chain)
+  std::vector<cudaStream_t> grp_streams_; // capture streams of groups 1..G-1
+  cudaEvent_t fork_ev_ = nullptr;
+  std::vector<cudaEvent_t> join_ev_;
   cudaStream_t cap_stream_ = nullptr;
 
   // buffers referenced at run time
@@ -125,6 +138,8 @@ class Engine {
   int add_dense(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int act, const Tensor* res,
                 const Tensor& out, float* out_f32 = nullptr, int ld_f32 = 0, const float* gamma = nullptr,
                 const float* beta = nullptr);
+  bool stem_fused_ = false;               // the encode program starts with stem_kernel (needs 16-byte aligned images)
+  bool use_stem_ = true;                  // FPNMT_STEM=0: explicit im2col + GEMM stem (always in BF16X3 mode)
   bool use_xattn_ = true;                 // FPNMT_XATTN=0: separate q2 / cross-attention / o2+LN kernels (always in BF16X3 mode)
   bool use_tgemm_ = true;                 // FPNMT_TGEMM=0 routes the decoder GEMMs through igemm + separate LayerNorm
   int build_stem_resnet_like(Program& p, const std::string& conv_key, const std::string& bn_key, float eps, Tensor* out);

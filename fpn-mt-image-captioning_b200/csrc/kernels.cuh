@@ -41,9 +41,10 @@ int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s);
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
                          int out_col, cudaStream_t s);
 // Decoder self-attention, one new position per row, KV cache with beam-ancestry indirection.
-// qkv: [rows][3*d] (q|k|v) of the new position; caches [rows][T][d]; anc [rows][T] physical row per position.
-int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, const int* step, int rows, int T,
-                              int heads, Act out, cudaStream_t s);
+// qkv: [rows][3*d] (q|k|v) of the new position; caches [rows][T][d]; anc [2][..][T] physical row per position, the two
+// step parities `anc_stride` ints apart (rows may be a slice of a larger batch: anc_stride = total rows * T).
+int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, size_t anc_stride, const int* step, int rows,
+                              int T, int heads, Act out, cudaStream_t s);
 // Decoder cross-attention over the 16 memory tokens of the row's image.
 int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam, int Tk, int heads, Act out,
                                cudaStream_t s);
@@ -51,6 +52,7 @@ int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, in
 // ---- beam.cu ------------------------------------------------------------------------------------
 struct BeamState {
   int B, N, V, T;            // images, beam width, vocab, max steps
+  int Btot;                  // images of the whole batch when this state is a slice of it (stride of the [T][..] logs)
   int start_id, end_id;
   int prob_mode;             // 1: product of probabilities (reference), 0: sum of log-probs
   float* score[2];           // [B*N] double-buffered beam scores

@@ -55,7 +55,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
-  const int opnd = p.layer * p.B + b;                 // which per-image operand set
+  const int opnd = p.layer * p.Btot + p.b0 + b;                 // which per-image operand set
 
   pdl_launch();
   if (warp == 0 && lane == 0) {
@@ -277,8 +277,8 @@ int xattn_launch(const XattnOp& op, cudaStream_t stream) {
   return 0;
 }
 
-int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int beam, int layer, const float* sbias,
-                  const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out) {
+int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int Btot, int b0, int B, int beam, int layer,
+                  const float* sbias, const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out) {
   if (beam > XA_NROWS || x.C != 512 || x.lo || out.lo) {
     set_last_error("make_xattn_op: needs beam <= 16, d_model == 512 and plain bf16 activations");
     return 1;
@@ -286,6 +286,8 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int
   XattnParams& p = op->p;
   p = XattnParams{};
   p.B = B;
+  p.b0 = b0;
+  p.Btot = Btot;
   p.beam = beam;
   p.R = B * beam;
   p.layer = layer;
@@ -296,9 +298,9 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int
   p.eps = 1e-6f;
   p.res = x;
   p.out = out;
-  int rc = encode_tmap_2d(&op->tmM, Mt, 512, (uint64_t)L * B * 128, 512, 128);
+  int rc = encode_tmap_2d(&op->tmM, Mt, 512, (uint64_t)L * Btot * 128, 512, 128);
   if (rc) return rc;
-  rc = encode_tmap_2d(&op->tmN, Nt, 128, (uint64_t)L * B * 512, 128, 128);
+  rc = encode_tmap_2d(&op->tmN, Nt, 128, (uint64_t)L * Btot * 512, 128, 128);
   if (rc) return rc;
   return encode_tmap_2d(&op->tmX, x.p, 512, (uint64_t)B * beam, (uint64_t)x.ld, XA_NROWS);
 }

@@ -20,7 +20,8 @@ constexpr int XA_NROWS = 16;        // UMMA N: beam rows of one image, padded to
 constexpr int XA_PAIRS = 128;       // heads x memory tokens
 
 struct XattnParams {
-  int B, beam, R;            // images, beam width (<= 16), rows = B * beam
+  int B, beam, R;            // images of this launch, beam width (<= 16), rows = B * beam
+  int b0, Btot;              // first image of this launch within the batch, images of the whole batch (operand index)
   int layer;                 // decoder layer (selects the per-image operands)
   const float* sbias;        // [L][B][128] score bias (bq . K / 8; -1e30 for padded tokens)
   const float* obias;        // [512] output-projection bias of this layer
@@ -40,8 +41,9 @@ size_t xattn_smem_bytes();
 int xattn_set_attributes();
 int xattn_launch(const XattnOp& op, cudaStream_t stream);
 // Mt: [L*B*128][512] bf16, Nt: [L*B*512][128] bf16, x: out1 view.
-int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int B, int beam, int layer, const float* sbias,
-                  const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out);
+// x / out are the row views of images [b0, b0 + B) of a batch of Btot images.
+int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int Btot, int b0, int B, int beam, int layer,
+                  const float* sbias, const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out);
 
 // Folding kernels (once per batch, all layers): ckv = cross K/V activations [B*n_mem][L*2*512] (K at l*1024, V at +512).
 int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const float* const* wq, const float* const* bq,

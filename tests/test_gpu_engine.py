@@ -353,3 +353,50 @@ def test_double_buffered_host_input_matches_one_shot_generate():
     with pytest.raises(ValueError):
         eng.stage(torch.zeros(B, S, S, 3).cuda(), 0)
     eng.close()
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+def test_decoder_groups_match_single_chain(groups):
+    """FPNMT_DEC_GROUPS cuts the batch into independent decode chains (parallel branches of the decode graph over row
+    slices of the same buffers): identical ids, lengths and per-step scores as the single chain."""
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=8)
+    img = O.test_images(5, S, seed=12).cuda()
+    res = {}
+    try:
+        for g in (1, groups):
+            os.environ["FPNMT_DEC_GROUPS"] = str(g)
+            eng = Engine(w, backbone=bb, batch=5, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
+                         use_graphs=True)
+            res[g] = eng.generate(img, early_stop=False, return_scores=True)
+            again = eng.generate(img, early_stop=False)
+            assert torch.equal(again[0], res[g][0])
+            eng.close()
+    finally:
+        os.environ.pop("FPNMT_DEC_GROUPS", None)
+    assert torch.equal(res[1][0], res[groups][0]) and torch.equal(res[1][1], res[groups][1])
+    assert torch.allclose(res[1][2].cpu(), res[groups][2].cpu(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("bb", BACKBONES)
+def test_fused_stem_matches_im2col_path(bb):
+    """stem_kernel (image -> im2col tile built in shared memory -> tcgen05) vs the explicit im2col + GEMM stem: same bf16
+    operands and fp32 accumulation, only the summation order differs, so the first backbone taps agree to bf16 rounding."""
+    from fpnmt.engine import Engine
+    w = small_weights(bb, V, L, seed=5)
+    img = O.test_images(3, 512, seed=17).cuda()
+    taps = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["FPNMT_STEM"] = mode
+            eng = Engine(w, backbone=bb, batch=3, beam=N, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16",
+                         use_graphs=False)
+            eng.encode(img)
+            taps[mode] = {n: eng.tap(n).cpu() for n in ("C3", "C5", "P3")}
+            eng.close()
+    finally:
+        os.environ.pop("FPNMT_STEM", None)
+    assert rel(taps["1"]["C3"], taps["0"]["C3"]) < 1e-2
+    assert rel(taps["1"]["P3"], taps["0"]["P3"]) < 3e-2
+    assert torch.isfinite(taps["1"]["C5"]).all()
