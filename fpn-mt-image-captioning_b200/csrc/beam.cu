@@ -88,21 +88,31 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   const int nv4 = (V + 4 * THREADS - 1) / (4 * THREADS);  // float4 slots per thread; slot i of thread tid = elements
   float* s_row = reinterpret_cast<float*>(s_row4);        //   (i*THREADS + tid)*4 .. +3 (conflict-free, coalesced)
 
-  // ---- stage the row in shared memory (registers stay small: every row block of the step is resident at once)
+  // ---- stage the row in shared memory with 16-byte cp.async: every load of the row is in flight at once and no
+  // registers are tied up (every row block of the step is resident at the same time); then one pass for the maxima
+  {
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_row4);
+#pragma unroll 4
+    for (int i = 0; i < nv4; ++i) {
+      const int e = (i * THREADS + tid) * 4;
+      if (e + 3 < V) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + (uint32_t)(i * THREADS + tid) * 16u), "l"(x + e) : "memory");
+      } else {
+        float4 q;
+        q.x = (e < V) ? x[e] : -INFINITY;
+        q.y = (e + 1 < V) ? x[e + 1] : -INFINITY;
+        q.z = (e + 2 < V) ? x[e + 2] : -INFINITY;
+        q.w = (e + 3 < V) ? x[e + 3] : -INFINITY;
+        s_row4[i * THREADS + tid] = q;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   float m = -INFINITY;
 #pragma unroll 4
   for (int i = 0; i < nv4; ++i) {
-    const int e = (i * THREADS + tid) * 4;
-    float4 q;
-    if (e + 3 < V) {
-      q = __ldcs(reinterpret_cast<const float4*>(x + e));
-    } else {
-      q.x = (e < V) ? x[e] : -INFINITY;
-      q.y = (e + 1 < V) ? x[e + 1] : -INFINITY;
-      q.z = (e + 2 < V) ? x[e + 2] : -INFINITY;
-      q.w = (e + 3 < V) ? x[e + 3] : -INFINITY;
-    }
-    s_row4[i * THREADS + tid] = q;
+    const float4 q = s_row4[i * THREADS + tid];               // own slots only: no barrier needed
     m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
   }
   const float tmax_v = m;                                  // this thread's largest logit

@@ -977,6 +977,13 @@ int Engine::build_decoder() {
         if (xattn) {
           XattnOp xo;
           RC(make_xattn_op(&xo, xMt, xNt, L, B, b0, Bg, N, l, xSb, w.go2.bias, w.lnp[2], w.lnp[3], out1.a, out2.a));
+          if (const char* dn = getenv("FPNMT_DBG_OP")) {
+            if (ln + "_xattn" == dn) {
+              dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
+              cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+              xo.p.dbg = dbg_buf_;
+            }
+          }
           Op o;
           o.name = ln + "_xattn(q2+cross_attn+o2+res+ln)" + sfx;
           o.kind = "xattn";

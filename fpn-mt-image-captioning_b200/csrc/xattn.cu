@@ -57,6 +57,18 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   const int b = blockIdx.x;
   const int opnd = p.layer * p.Btot + p.b0 + b;                 // which per-image operand set
 
+  __shared__ long long* s_dbg;
+  if (threadIdx.x == 0) {
+    s_dbg = nullptr;
+    if (p.dbg && blockIdx.x == 0) {
+      const long long inst = (long long)atomicAdd((unsigned long long*)p.dbg, 1ull);
+      s_dbg = p.dbg + 16 + (inst % 8) * 16;
+      long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+      s_dbg[0] = t_;
+    }
+  }
+#define XDBG(k) do { if (s_dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); s_dbg[k] = t_; } } while (0)
   pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmM);
@@ -89,6 +101,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
           tma_load_2d(sA2 + (ft * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128);
       }
       pdl_wait();
+      XDBG(1);
       mbar_expect_tx(fullB1, 8 * XA_CHUNK_B);
       for (int i = 0; i < 8; ++i) tma_load_2d(sB1 + i * XA_CHUNK_B, &tmX, fullB1, i * 64, b * p.beam);
       // feature tiles 2,3 of Nt_b go into the upper half of the Mt_b area as soon as chain 1 has consumed it, so their
@@ -105,7 +118,9 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     if (lane == 0) {
       // ---- chain 1: scores^T
       mbar_wait(fullA1, 0);
+      XDBG(2);
       mbar_wait(fullB1, 0);
+      XDBG(3);
       tc_fence_after();
       {
         const uint64_t a0 = umma_desc_sw128(smem_u32(sA1));
@@ -118,12 +133,15 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
                       (i > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(tfull1);
+      XDBG(4);
       // ---- chain 2: outputs^T, four feature tiles of 128
       mbar_wait(pready, 0);
+      XDBG(7);
       tc_fence_after();
       const uint64_t pb0 = umma_desc_sw128(smem_u32(sB2));
       for (int ft = 0; ft < 4; ++ft) {
         mbar_wait(&fullA2[ft], 0);
+        if (ft == 2) XDBG(8);
         tc_fence_after();
         const uint64_t a0 = umma_desc_sw128(smem_u32(ft < 2 ? sA2 + ft * 2 * XA_CHUNK_A : sA1 + (4 + (ft - 2) * 2) * XA_CHUNK_A));
 #pragma unroll
@@ -134,6 +152,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
                       pb0 + (uint64_t)(c * (XA_CHUNK_B >> 4) + 2 * k), IDESC, (c > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(tfull2);
+      XDBG(9);
     }
     __syncwarp();
   } else {
@@ -157,31 +176,35 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     // ---- softmax over the 16 tokens of this head, for each of the 16 row columns
     mbar_wait(tfull1, 0);
     tc_fence_after();
+    if (t == 0) XDBG(5);
     {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16), r);
       tmem_ld_wait();
-      float pr[16];
+      // All 16 columns are processed unconditionally (the padding columns hold finite rows of the next image or zeros)
+      // so that the 16 independent shuffle chains interleave; padding columns are zeroed at the end.
+      float sc[16], mx[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        if (c >= p.beam) {                        // padding columns (rows of the next image): never read back
-          pr[c] = 0.f;
-          continue;
-        }
-        const float s = __uint_as_float(r[c]) + sb;
-        float m = s;
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        const float ex = __expf(s - m);
-        float sum = ex;
-        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        pr[c] = ex / sum;
+        sc[c] = __uint_as_float(r[c]) + sb;
+        mx[c] = sc[c];
       }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+      float pr[16], sm[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        pr[c] = __expf(sc[c] - mx[c]);
+        sm[c] = pr[c];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) sm[c] += __shfl_xor_sync(0xffffffffu, sm[c], o);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pr[c] = c < p.beam ? __fdividef(pr[c], sm[c]) : 0.f;
       // P^T[row c][k = L]: K-major rows of 128 B, 16-byte units XOR-swizzled with (row & 7)
       uint8_t* base = sB2 + (L >> 6) * XA_CHUNK_B + (L & 7) * 2;
       const int unit = (L & 63) >> 3;
@@ -191,10 +214,12 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     }
     fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
     mbar_arrive(pready);
+    if (t == 0) XDBG(6);
     // ---- outputs: + bias, transpose through the scratch (aliases the Mt_b area, free since chain 1 completed)
     float* scr = reinterpret_cast<float*>(sA1);
     mbar_wait(tfull2, 0);
     tc_fence_after();
+    if (t == 0) XDBG(10);
 #pragma unroll 1
     for (int ft = 0; ft < 4; ++ft) {
       uint32_t r[16];
@@ -206,6 +231,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
       for (int c = 0; c < 16; ++c) scr[c * XA_SCR_STRIDE + f] = __uint_as_float(r[c]) + ob;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t == 0) XDBG(11);
     // ---- residual + LayerNorm over 512 features: 8 threads per row, 64 features each (Chan's parallel variance)
     float x[64];
 #pragma unroll
@@ -259,6 +285,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     }
   }
 
+  if (threadIdx.x == 64) XDBG(12);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -30,6 +30,7 @@ struct XattnParams {
   float eps;
   Act res;                   // out1 [R][512] (also the B operand of the first GEMM, through tmX)
   Act out;                   // out2 [R][512]
+  long long* dbg;            // optional globaltimer stamps (FPNMT_DBG_OP), else nullptr
 };
 
 struct XattnOp {
