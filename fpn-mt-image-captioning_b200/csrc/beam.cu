@@ -77,10 +77,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   __shared__ int s_ci[NW * 32];
   __shared__ int s_parent[32], s_token[32];
   __shared__ int s_last;
-  pdl_launch();
-  pdl_wait();
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long* dbg = (st.dbg && row < st.N) ? st.dbg + 16 : nullptr;       // timeline of image 0 (its last block: phase 2)
+#define BDBG(k) do { if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[k] = t_; } } while (0)
+  if (row == 0) BDBG(0);
+  pdl_launch();
+  pdl_wait();
+  if (row == 0) BDBG(1);
   const int V = st.V, N = st.N, T = st.T;
   const int t = *st.step;
   const float score = st.score[t & 1][row];
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+  if (row == 0) BDBG(2);
   float m = -INFINITY;
 #pragma unroll 4
   for (int i = 0; i < nv4; ++i) {
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   __shared__ int s_cnt;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
+  if (row == 0) BDBG(3);
   m = s_m[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) m = fmaxf(m, s_m[w]);
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     }
   }
   __syncthreads();
+  if (row == 0) BDBG(4);
   const int cnt = s_cnt;
   if (cnt <= CAP && cnt >= N) {
     if (tid < cnt) {
@@ -286,12 +293,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     }
   }
   __syncthreads();
+  if (row == 0) BDBG(5);
   if (tid == 0) {
     __threadfence();                                        // candidates visible before the image counter moves
     s_last = (atomicAdd(st.img_count + row / N, 1) == N - 1);
   }
   __syncthreads();
+  if (row == 0) BDBG(6);
   if (!s_last) return;
+  BDBG(7);
 
   // =================================================================== phase 2: this block closes image b
   __threadfence();
@@ -314,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     s_ff[c] = ok ? (c / N) * V + tok : 0x7fffffff;          // flat index over the N x V candidates
   }
   __syncthreads();
+  BDBG(8);
   for (int c = tid; c < NN; c += THREADS) {
     const int f = s_ff[c];
     if (f == 0x7fffffff) continue;
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     }
   }
   __syncthreads();
+  BDBG(9);
   for (int n = warp; n < N; n += NW) {
     const int par = s_parent[n], tok = s_token[n];
     const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
@@ -346,6 +358,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       danc[t] = rows0 + par;
     }
   }
+  BDBG(10);
   // next step's decoder input: x[row] = embedding[token] + pos[t + 1]   (transformer.py:326-329)
   if (em.emb && t + 1 < T) {
     const int groups = em.D / 8;
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     }
   }
   __syncthreads();
+  BDBG(11);
   // top beam is rank 0 (scores are sorted; tf.argmax returns the first maximum) — pipeline.py:143-148
   if (warp == 0) {
     const int top_tok = s_token[0];
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       }
     }
   }
+  BDBG(12);
 }
 int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s) {
   if (st.N > 32 || (ld & 3)) {

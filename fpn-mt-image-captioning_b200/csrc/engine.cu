@@ -1022,6 +1022,13 @@ int Engine::build_decoder() {
       }
       return 0;
     };
+    if (const char* dn = getenv("FPNMT_DBG_OP")) {
+      if (std::string(dn) == "beam_step") {
+        dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
+        cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+        bs_.dbg = dbg_buf_;
+      }
+    }
     RC(build_chain(0, B, bs_, embed_prog_, step_prog_, &beam_embed_));
 
     // ---- decoder groups (opt-in, FPNMT_DEC_GROUPS=G): G independent chains over image slices, run as parallel branches

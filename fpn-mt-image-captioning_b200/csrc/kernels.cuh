@@ -70,6 +70,7 @@ struct BeamState {
   float* step_logprob;       // optional [T][B] log-prob (or prob) increment of the chosen top beam, may be null
   int* parent_out;           // optional [T][B*N] parents chosen per step (debug / parity), may be null
   int* token_out;            // optional [T][B*N]
+  long long* dbg;            // optional globaltimer stamps of image 0 (FPNMT_DBG_OP=beam_step), else nullptr
 };
 // true_beam = 0 reproduces the reference (all beams start identical, pipeline.py:101-102); 1 starts beams 1..N-1 dead
 int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s);

@@ -39,17 +39,19 @@ struct StemCfg {
   static constexpr int PROWF = PV * 4;
   static constexpr int SROWS = ST_TH + KS - 1;                         // space-to-depth patch rows
   static constexpr int SPX = ST_TW + KS - 1;                           //                      pixels per row (24 B each)
+  static constexpr int SPITCH = 68;                                    // row pitch in pixels: 6*68 = 24 (mod 32) words keeps
+                                                                       // the 8-byte gathers of the im2col copy conflict-free
   static constexpr int W_CHUNK = COUT * 128;
   static constexpr int OFF_A = KCH * W_CHUNK;
   static constexpr int OFF_IN = OFF_A + 2 * KCH * ST_A_CHUNK;
   static constexpr int OFF_S2D = OFF_IN + 2 * PROWS * PROWF * 4;
-  static constexpr int OFF_OUT = (OFF_S2D + SROWS * SPX * 24 + 15) / 16 * 16;
+  static constexpr int OFF_OUT = (OFF_S2D + SROWS * SPITCH * 24 + 15) / 16 * 16;
   static constexpr int OFF_BIAS = OFF_OUT + 4 * 32 * COUT * 2;
   static constexpr int OFF_BARS = OFF_BIAS + COUT * 4;
   static constexpr int SMEM = OFF_BARS + 128 + 1024;
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static_assert(W_CHUNK % 1024 == 0 && OFF_IN % 16 == 0 && OFF_S2D % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
-  static_assert(KTOT % 16 == 0 && SEG % 8 == 0 && COUT % 32 == 0 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "shape");
+  static_assert(SPITCH >= SPX && KTOT % 16 == 0 && SEG % 8 == 0 && COUT % 32 == 0 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "shape");
 };
 
 __device__ __forceinline__ void st_cp16(uint32_t dst, const void* src, bool valid) {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
         const float2* r0 = reinterpret_cast<const float2*>(sp + (2 * sy) * C::PROWF + 6 * sx);
         const float2* r1 = reinterpret_cast<const float2*>(sp + (2 * sy + 1) * C::PROWF + 6 * sx);
         const float2 a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2];
-        uint2* d = reinterpret_cast<uint2*>(sS + (size_t)i * 24);
+        uint2* d = reinterpret_cast<uint2*>(sS + (size_t)(sy * C::SPITCH + sx) * 24);
         d[0] = make_uint2(st_pack(a0.x, a0.y), st_pack(a1.x, a1.y));
         d[1] = make_uint2(st_pack(a2.x, a2.y), st_pack(b0.x, b0.y));
         d[2] = make_uint2(st_pack(b1.x, b1.y), st_pack(b2.x, b2.y));
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int row = r0 + 32 * j;
-            const uint2* src = reinterpret_cast<const uint2*>(sS + ((size_t)((row >> 6) + kyp) * C::SPX + (row & 63)) * 24 + part * 16);
+            const uint2* src = reinterpret_cast<const uint2*>(sS + ((size_t)((row >> 6) + kyp) * C::SPITCH + (row & 63)) * 24 + part * 16);
             lo[c][j] = src[0];
             hi[c][j] = src[1];
           }
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
           const int idx = ptid + j * ST_PROD;
           const int row = idx / C::UNITS, u = idx - row * C::UNITS;
           const int kyp = u / C::SEGU, part = u - kyp * C::SEGU;
-          const uint2* src = reinterpret_cast<const uint2*>(sS + ((size_t)((row >> 6) + kyp) * C::SPX + (row & 63)) * 24 + part * 16);
+          const uint2* src = reinterpret_cast<const uint2*>(sS + ((size_t)((row >> 6) + kyp) * C::SPITCH + (row & 63)) * 24 + part * 16);
           if (idx < 128 * C::UNITS) {
             lo[j] = src[0];
             hi[j] = src[1];
