@@ -19,7 +19,8 @@ constexpr int XA_OFF_B1 = XA_OFF_A2 + 4 * XA_CHUNK_A;    // 8 chunks (out1 rows)
 constexpr int XA_OFF_B2 = XA_OFF_B1 + 8 * XA_CHUNK_B;    // 2 chunks (P^T)
 constexpr int XA_OFF_PART = XA_OFF_B2 + 2 * XA_CHUNK_B;  // float2 [8][16]
 constexpr int XA_OFF_BARS = XA_OFF_PART + 8 * 16 * 8;
-constexpr int XA_SCR_STRIDE = 513;                       // floats per row of the transposed output scratch
+constexpr int XA_SCR_STRIDE = 516;                       // floats per row of the transposed output scratch (16 B aligned
+                                                         // rows, 4-bank skew: float4 reads of 8 consecutive rows are conflict-free)
 constexpr int XA_TMEM_COLS = 128;
 
 size_t xattn_smem_bytes() { return XA_OFF_BARS + 256 + 1024; }
@@ -220,22 +221,28 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     mbar_wait(tfull2, 0);
     tc_fence_after();
     if (t == 0) XDBG(10);
-#pragma unroll 1
-    for (int ft = 0; ft < 4; ++ft) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + 32 + ft * XA_NROWS, r);
+    {
+      uint32_t r[2][32];                          // the four 16-column accumulators are contiguous: two 32-column loads
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 32, r[0]);
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 64, r[1]);
       tmem_ld_wait();
-      const int f = ft * 128 + L;
-      const float ob = __ldg(p.obias + f);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) scr[c * XA_SCR_STRIDE + f] = __uint_as_float(r[c]) + ob;
+      for (int ft = 0; ft < 4; ++ft) {
+        const int f = ft * 128 + L;
+        const float ob = __ldg(p.obias + f);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) scr[c * XA_SCR_STRIDE + f] = __uint_as_float(r[ft >> 1][(ft & 1) * 16 + c]) + ob;
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (t == 0) XDBG(11);
     // ---- residual + LayerNorm over 512 features: 8 threads per row, 64 features each (Chan's parallel variance)
     float x[64];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) x[i] = scr[lrow * XA_SCR_STRIDE + part * 64 + i];
+    for (int i = 0; i < 16; ++i) {
+      const float4 q = *reinterpret_cast<const float4*>(scr + lrow * XA_SCR_STRIDE + part * 64 + i * 4);
+      x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+    }
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       float tt[8];
