@@ -321,7 +321,9 @@ __global__ void k_coattention(Act score, Act cls, int HW, int pix_per_block, Act
   }
 }
 int launch_coattention(Act score, Act cls, int N, int HW, Act out, cudaStream_t s) {
-  const int ppb = 32;
+  // every block recomputes the image's softmax statistics (2 passes over HW scores): larger pixel chunks for the large maps
+  // keep that overhead below the scaling work itself
+  const int ppb = HW >= 4096 ? 256 : HW >= 1024 ? 128 : 32;
   dim3 grid((HW + ppb - 1) / ppb, N);
   FPNMT_CUDA_OK(launch_k(k_coattention, dim3(grid), dim3(256), 0, s, score, cls, HW, ppb, out));
   LAUNCH_CHECK();
@@ -351,12 +353,19 @@ __device__ __forceinline__ void ln_row_512(LoadFn load, const float* __restrict_
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = h * 256 + lane * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (add) {
+      a0 = __ldg(reinterpret_cast<const float4*>(add + c));
+      a1 = __ldg(reinterpret_cast<const float4*>(add + c + 4));
+    }
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = (v[h * 8 + i] - mean) * rstd * gamma[c + i] + beta[c + i];
-      if (add) o[i] += add[c + i];
-    }
+    for (int i = 0; i < 8; ++i) o[i] = ((v[h * 8 + i] - mean) * rstd * gg[i] + bb[i]) + aa[i];
     st_act8(out, orow, c, o);
   }
 }
