@@ -27,6 +27,9 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import subprocess
 import sys
 import threading
