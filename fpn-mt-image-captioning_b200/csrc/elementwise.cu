@@ -98,10 +98,14 @@ int launch_im2col_stem(const float* const* img, int N, int H, int W, int kh, int
 }
 
 // ---------------------------------------------------------------------------------------- pooling
-__global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+// K = compile-time window (2 or 3; 0 = generic run-time window): the fixed-size variants are fully unrolled so that all
+// window loads are issued back to back.
+template <int K>
+__global__ void k_maxpool(Act in, int N, int H, int W, int k_rt, int stride, int pad_t, int pad_l, int Ho, int Wo,
                           int zero_pad, Act out) {
   pdl_launch();
   pdl_wait();
+  const int k = K ? K : k_rt;
   const int groups = in.C / 8;
   const size_t total = (size_t)N * Ho * Wo * groups;
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -114,21 +118,56 @@ __global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pa
   float m[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-  for (int ky = 0; ky < k; ++ky) {
-    const int y = yo * stride + ky - pad_t;
-    for (int kx = 0; kx < k; ++kx) {
-      const int x = xo * stride + kx - pad_l;
-      if (y < 0 || y >= H || x < 0 || x >= W) {
-        if (zero_pad) {
+  if constexpr (K != 0) {
+    uint4 raw[K * K];
+    bool ok[K * K];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
-        }
-        continue;
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int y = yo * stride + ky - pad_t, x = xo * stride + kx - pad_l;
+        ok[ky * K + kx] = y >= 0 && y < H && x >= 0 && x < W;
+        raw[ky * K + kx] = ok[ky * K + kx] ? *reinterpret_cast<const uint4*>(in.p + (((size_t)n * H + y) * W + x) * in.ld + g * 8)
+                                          : make_uint4(0u, 0u, 0u, 0u);
       }
-      float v[8];
-      ld_act8(in, ((size_t)n * H + y) * W + x, g * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+    for (int t = 0; t < K * K; ++t) {
+      if (ok[t]) {
+        float v[8];
+        unpack8(raw[t], v);
+        if (in.lo) {
+          // split activations: add the low halves (rare path: BF16X3 mode)
+          float lo[8];
+          const int ky = t / K, kx = t % K;
+          const int y = yo * stride + ky - pad_t, x = xo * stride + kx - pad_l;
+          unpack8(*reinterpret_cast<const uint4*>(in.p + in.lo + (((size_t)n * H + y) * W + x) * in.ld + g * 8), lo);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += lo[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+      } else if (zero_pad) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+      }
+    }
+  } else {
+    for (int ky = 0; ky < k; ++ky) {
+      const int y = yo * stride + ky - pad_t;
+      for (int kx = 0; kx < k; ++kx) {
+        const int x = xo * stride + kx - pad_l;
+        if (y < 0 || y >= H || x < 0 || x >= W) {
+          if (zero_pad) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+          }
+          continue;
+        }
+        float v[8];
+        ld_act8(in, ((size_t)n * H + y) * W + x, g * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+      }
     }
   }
   st_act8(out, pix, g * 8, m);
@@ -136,7 +175,13 @@ __global__ void k_maxpool(Act in, int N, int H, int W, int k, int stride, int pa
 int launch_maxpool(Act in, int N, int H, int W, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, bool zero_pad,
                    Act out, cudaStream_t s) {
   const size_t total = (size_t)N * Ho * Wo * (in.C / 8);
-  FPNMT_CUDA_OK(launch_k(k_maxpool, dim3(nblocks(total, 256)), dim3(256), 0, s, in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out));
+  const dim3 grid(nblocks(total, 256));
+  if (k == 3)
+    FPNMT_CUDA_OK(launch_k(k_maxpool<3>, grid, dim3(256), 0, s, in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out));
+  else if (k == 2)
+    FPNMT_CUDA_OK(launch_k(k_maxpool<2>, grid, dim3(256), 0, s, in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out));
+  else
+    FPNMT_CUDA_OK(launch_k(k_maxpool<0>, grid, dim3(256), 0, s, in, N, H, W, k, stride, pad_t, pad_l, Ho, Wo, zero_pad ? 1 : 0, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -266,6 +311,88 @@ int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const flo
   const size_t total = pixels * (in.C / 8);
   FPNMT_CUDA_OK(launch_k(k_scale_shift_relu, dim3(nblocks(total, 256)), dim3(256), 0, s, in, pixels, scale, shift, out));
   LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- 3x3 convolution to ONE channel
+// The co-attention score map (retinanet.py:287, Conv2D(1, 3x3, same) on a 256-channel map) as a CUDA-core kernel: a
+// 1-output-channel GEMM wastes 31/32 of the smallest tensor-core tile (the igemm version ran at 5-8 TFLOP/s).  Block = 8x8
+// output pixels; the 10x10x256 bf16 halo is staged in shared memory (pixel pitch 576 B: conflict-free 16-byte reads);
+// lane = one 8-channel unit whose 9x8 weights live in registers, warp = one row of 8 pixels; each halo value is loaded
+// once per row and used by the up to three pixels whose windows contain it; lanes are summed with shuffles.
+constexpr int SC_C = 256, SC_PITCH = 576, SC_TILE = 8, SC_HALO = SC_TILE + 2;
+__global__ void __launch_bounds__(256) k_conv3x3_c1(Act in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                    int N, int H, int W, Act out) {
+  extern __shared__ __align__(16) uint8_t s_halo[];
+  pdl_launch();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wr[9][8];                                            // weights of this lane's channel unit (static: before the wait)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w + t * SC_C + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w + t * SC_C + lane * 8 + 4));
+    wr[t][0] = a.x; wr[t][1] = a.y; wr[t][2] = a.z; wr[t][3] = a.w;
+    wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
+  }
+  const float bv = __ldg(bias);
+  pdl_wait();
+  const int x0 = blockIdx.x * SC_TILE, y0 = blockIdx.y * SC_TILE, n = blockIdx.z;
+  for (int i = threadIdx.x; i < SC_HALO * SC_HALO * 32; i += 256) {
+    const int px = i >> 5, u = i & 31;
+    const int hy = px / SC_HALO, hx = px - hy * SC_HALO;
+    const int y = y0 + hy - 1, x = x0 + hx - 1;
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const bf16* src = ok ? in.p + (((size_t)n * H + y) * W + x) * in.ld + u * 8 : in.p;
+    const int sz = ok ? 16 : 0;                              // src-size 0: zero fill (the "same" padding)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(s_halo + px * SC_PITCH + u * 16)),
+                 "l"(src), "r"(sz) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int yl = warp;                                       // output row of the tile
+  float acc[SC_TILE];
+#pragma unroll
+  for (int i = 0; i < SC_TILE; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+    for (int hx = 0; hx < SC_HALO; ++hx) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(s_halo + ((yl + dy) * SC_HALO + hx) * SC_PITCH + lane * 16), f);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xl = hx - dx;                              // output pixel whose tap (dy, dx) reads halo column hx
+        if (xl >= 0 && xl < SC_TILE) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[xl] = fmaf(f[c], wr[dy * 3 + dx][c], acc[xl]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SC_TILE; ++i) acc[i] = warp_sum(acc[i]);
+  const int y = y0 + yl;
+  if (lane < SC_TILE && y < H && x0 + lane < W) {
+    float v = acc[0];
+#pragma unroll
+    for (int i = 1; i < SC_TILE; ++i) v = (lane == i) ? acc[i] : v;
+    st_act(out, ((size_t)n * H + y) * W + x0 + lane, 0, v + bv);
+  }
+}
+int launch_conv3x3_c1(Act in, const float* w, const float* bias, int N, int H, int W, Act out, cudaStream_t s) {
+  if (in.C != SC_C || in.lo || out.lo) {
+    set_last_error("conv3x3_c1: needs a plain bf16 256-channel input");
+    return 1;
+  }
+  static bool attr_done = false;
+  const size_t smem = (size_t)SC_HALO * SC_HALO * SC_PITCH;
+  if (!attr_done) {
+    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_c1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const dim3 grid((W + SC_TILE - 1) / SC_TILE, (H + SC_TILE - 1) / SC_TILE, N);
+  FPNMT_CUDA_OK(launch_k(k_conv3x3_c1, grid, dim3(256), smem, s, in, w, bias, N, H, W, out));
   return 0;
 }
 

@@ -665,6 +665,11 @@ int Engine::build_fpn_heads(Program& p, Tensor c[3]) {
   RC(prep_conv(RN + "/regression_submodel/pyramid_regression_1/kernel", RN + "/regression_submodel/pyramid_regression_1/bias", "", 0, &r1w));
   RC(prep_conv(RN + "/classification_submodel/pyramid_classification_1/kernel", RN + "/classification_submodel/pyramid_classification_1/bias", "", 0, &c1w));
   RC(prep_conv(HM + "/conv2d_2/kernel", HM + "/conv2d_2/bias", "", 0, &scw));
+  float *score_w = nullptr, *score_b = nullptr;      // fp32 [9][256] (HWIO with O = 1 is already tap-major) + bias
+  if (!split_ && F == 256) {
+    RC(prep_vec(HM + "/conv2d_2/kernel", &score_w));
+    RC(prep_vec(HM + "/conv2d_2/bias", &score_b));
+  }
   RC(prep_conv(HM + "/conv2d_3/kernel", HM + "/conv2d_3/bias", "", 0, &clw));
   RC(prep_conv(HM + "/conv2d_4/kernel", HM + "/conv2d_4/bias", "", 0, &h4w));
   RC(prep_conv(HM + "/conv2d_5/kernel", HM + "/conv2d_5/bias", "", 0, &h5w));
@@ -678,7 +683,17 @@ int Engine::build_fpn_heads(Program& p, Tensor c[3]) {
     RC(add_conv(p, L + "_reg1", chan_view(t0, 0, F), r1w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, r1));
     RC(add_conv(p, L + "_cls1", chan_view(t0, F, F), c1w, 3, 3, 1, 1, ACT_RELU, RES_NONE, nullptr, c1));
     Tensor score = new_act(B, x.H, x.W, 1), cmap = new_act(B, x.H, x.W, F);
-    RC(add_conv(p, L + "_score", r1, scw, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, score));
+    if (score_w) {   // bf16 mode: dedicated CUDA-core kernel (a 1-channel GEMM wastes the tensor-core tile)
+      Act ia = r1.a, oa = score.a;
+      const int hh = x.H, ww = x.W;
+      const float *sw = score_w, *sb = score_b;
+      Op o = ew_op(L + "_score", [=](cudaStream_t s) { return launch_conv3x3_c1(ia, sw, sb, B, hh, ww, oa, s); },
+                   (double)r1.pixels() * F * 2 + (double)score.pixels() * 2);
+      o.flops = 2.0 * (double)r1.pixels() * 9.0 * F;
+      p.push_back(std::move(o));
+    } else {
+      RC(add_conv(p, L + "_score", r1, scw, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, score));
+    }
     RC(add_conv(p, L + "_clsmap", c1, clw, 3, 3, 1, 1, ACT_NONE, RES_NONE, nullptr, cmap));
     Tensor co = new_act(B, x.H, x.W, F);
     {

@@ -21,6 +21,8 @@ int launch_depthwise3x3(Act in, int N, int H, int W, int stride, int pad_t, int 
 int launch_scale_shift_relu(Act in, size_t pixels, const float* scale, const float* shift, Act out, cudaStream_t s);
 // CoAttention_CNN: out[b,p,c] = softmax_p(score[b,:])[p] * cls[b,p,c]
 int launch_coattention(Act score, Act cls, int N, int HW, Act out, cudaStream_t s);
+// 3x3 "same" convolution of a 256-channel bf16 map to ONE channel (the co-attention score), w = fp32 [9][256], bias [1]
+int launch_conv3x3_c1(Act in, const float* w, const float* bias, int N, int H, int W, Act out, cudaStream_t s);
 // Encoder pre-amble: out[b*HW+p] = LN(in[b*HW+p]) + pos[p]   (C = 512)
 int launch_tokens_ln_pos(Act in, int N, int HW, const float* gamma, const float* beta, float eps, const float* pos,
                          Act out, cudaStream_t s);
