@@ -120,12 +120,15 @@ def _dec_step_cached(w: W, tok: torch.Tensor, pos_row: torch.Tensor, caches: Lis
 
 def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam: int, start_token: int,
                          end_token: int, num_layers: int = 6, num_heads: int = 8, early_stop: bool = True,
-                         trace: Optional[dict] = None) -> Tuple[np.ndarray, np.ndarray]:
+                         trace: Optional[dict] = None, true_beam: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """Batched KV-cached beam decode with log-domain scores.
 
     enc_output (B,16,d).  Returns (ids (B,max_seq_len) int32 padded with 0, lengths (B,) int32), each row being
     what `predict_reference` returns for that image (start stripped, trailing <end> stripped).
     An image stops the first time its top beam emits <end> (pipeline.py:147); stopped images are frozen.
+    true_beam=True is the flagged EXTENSION (not reference behaviour): only beam 0 is alive at t = 0
+    (log-score 0, the others -inf), so the N beams diverge instead of staying N copies of the greedy path
+    (pipeline.py:101-102 starts all N identical).
     """
     bsz, _, d = enc_output.shape
     rows = bsz * beam
@@ -139,6 +142,8 @@ def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam:
     caches = [{"k": None, "v": None} for _ in range(num_layers)]
     seqs = np.full((bsz, beam, 1), start_token, dtype=np.int64)
     score = np.zeros((bsz, beam), np.float32)
+    if true_beam:
+        score[:, 1:] = -np.inf
     done = np.zeros((bsz,), bool)
     out_ids = np.zeros((bsz, max_seq_len), np.int32)
     out_len = np.zeros((bsz,), np.int32)

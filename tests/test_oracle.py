@@ -157,3 +157,31 @@ def test_end_token_stops_and_is_stripped():
     assert lens.tolist() == [0, 0] and (ids == 0).all()        # pipeline.py:147-148 returns beam_result[1:-1] == []
     ref = O.predict_reference(None, O.W(w), T, N, 2, 3, num_layers=L, enc_output=mem[:1])
     assert len(ref) == 0
+
+
+def test_true_beam_extension_explores_and_never_scores_worse_than_greedy():
+    """Flagged extension: with only beam 0 alive at t = 0 the first step picks the N best DISTINCT
+    tokens of one distribution; on this fixture the returned sequence also scores at least as well as the reference's
+    degenerate (N x greedy) search (not a theorem for beam search in general: a fixture property)."""
+    L, V, T, N = 2, 96, 6, 4
+    w = small_weights("mobilenet224_1.0", V, L, seed=5)
+    Wv = O.W(w)
+    mem = torch.randn(3, 4, 512, generator=torch.Generator().manual_seed(3))
+    tr_true, tr_ref = {}, {}
+    ids_t, len_t = O.predict_batch_cached(mem, Wv, T, N, 2, 3, num_layers=L, early_stop=False, trace=tr_true, true_beam=True)
+    ids_r, len_r = O.predict_batch_cached(mem, Wv, T, N, 2, 3, num_layers=L, early_stop=False, trace=tr_ref)
+    assert ids_t.shape == ids_r.shape and len_t.tolist() == len_r.tolist()
+    for b in range(3):
+        lg0 = tr_true["logits"][0][b]                          # step-0 logits: all beams fed <start>, rows identical
+        assert np.allclose(lg0[0], lg0[1])
+        score0 = np.array([0.0] + [-np.inf] * (N - 1), np.float32)
+        parent, token, _ = O.beam_step(lg0, score0, "log")
+        assert parent.tolist() == [0] * N and len(set(token.tolist())) == N
+        assert token.tolist() == np.argsort(-lg0[0], kind="stable")[:N].tolist()
+
+    def seq_logprob(ids_row, b):                               # teacher-forced log-prob of a returned sequence
+        toks = torch.tensor([[2] + ids_row.tolist()])
+        lp = O.teacher_forced_logprobs(mem[b:b + 1], toks[:, :-1], Wv, T, L)[0]
+        return float(sum(lp[i, t] for i, t in enumerate(ids_row.tolist())))
+    for b in range(3):
+        assert seq_logprob(ids_t[b, :len_t[b]], b) >= seq_logprob(ids_r[b, :len_r[b]], b) - 1e-4
