@@ -341,20 +341,24 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int Btot, 
 
 // ------------------------------------------------------------------------------------------------ folding kernels
 // grid (B, heads = 8, L), 256 threads.  Keys/values of one (image, head, layer) are staged in shared memory as fp32.
-__global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const float* const* __restrict__ wq,
+// Both fold kernels process XF_IB images per block so that the 128 KB weight slice of a (layer, head) leaves L2 once per
+// XF_IB images (with one image per block the kernels moved 0.4-0.8 GB through L2 and took 209 + 156 us per batch).
+constexpr int XF_IB = 4;
+
+__global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int B, int n_mem, const float* const* __restrict__ wq,
                                                       const float* const* __restrict__ bq, bf16* __restrict__ Mt,
                                                       float* __restrict__ sbias) {
-  __shared__ __align__(16) float sK[16][64];
+  __shared__ __align__(16) float sK[XF_IB][16][64];
   pdl_launch();
   pdl_wait();
-  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
-  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-    const int j = i >> 6, d = i & 63;
-    sK[j][d] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + h * 64 + d]) : 0.f;
+  const int b0 = blockIdx.x * XF_IB, h = blockIdx.y, l = blockIdx.z;
+  for (int i = threadIdx.x; i < XF_IB * 16 * 64; i += blockDim.x) {
+    const int ib = i >> 10, j = (i >> 6) & 15, d = i & 63;
+    const int b = b0 + ib;
+    sK[ib][j][d] = (j < n_mem && b < B) ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + h * 64 + d]) : 0.f;
   }
   __syncthreads();
   const float* W = wq[l];                       // Dense kernel (in = k, out = h*64+d), row-major
-  bf16* dst = Mt + ((size_t)(l * B + b) * 128 + h * 16) * 512;
   for (int k = threadIdx.x; k < 512; k += blockDim.x) {
     float w[64];
 #pragma unroll
@@ -362,60 +366,84 @@ __global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int n_mem, const 
       const float4 v = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * 512 + h * 64 + d4 * 4));
       w[4 * d4] = v.x; w[4 * d4 + 1] = v.y; w[4 * d4 + 2] = v.z; w[4 * d4 + 3] = v.w;
     }
-    for (int j = 0; j < 16; ++j) {
-      float a = 0.f;
+    for (int ib = 0; ib < XF_IB; ++ib) {
+      if (b0 + ib >= B) break;
+      bf16* dst = Mt + ((size_t)(l * B + b0 + ib) * 128 + h * 16) * 512;
+#pragma unroll 1
+      for (int j0 = 0; j0 < 16; j0 += 4) {                   // four independent accumulation chains
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int d4 = 0; d4 < 16; ++d4) {                      // broadcast 16-byte shared loads
-        const float4 kq = *reinterpret_cast<const float4*>(&sK[j][d4 * 4]);
-        a = fmaf(kq.x, w[4 * d4], a);
-        a = fmaf(kq.y, w[4 * d4 + 1], a);
-        a = fmaf(kq.z, w[4 * d4 + 2], a);
-        a = fmaf(kq.w, w[4 * d4 + 3], a);
+        for (int d4 = 0; d4 < 16; ++d4) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {                   // broadcast 16-byte shared loads
+            const float4 kq = *reinterpret_cast<const float4*>(&sK[ib][j0 + jj][d4 * 4]);
+            a[jj] = fmaf(kq.x, w[4 * d4], a[jj]);
+            a[jj] = fmaf(kq.y, w[4 * d4 + 1], a[jj]);
+            a[jj] = fmaf(kq.z, w[4 * d4 + 2], a[jj]);
+            a[jj] = fmaf(kq.w, w[4 * d4 + 3], a[jj]);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) dst[(size_t)(j0 + jj) * 512 + k] = __float2bfloat16_rn(a[jj] * 0.125f);
       }
-      dst[(size_t)j * 512 + k] = __float2bfloat16_rn(a * 0.125f);
     }
   }
-  if (threadIdx.x < 16) {
-    const int j = threadIdx.x;
-    float a = 0.f;
-    for (int d = 0; d < 64; ++d) a = fmaf(sK[j][d], __ldg(bq[l] + h * 64 + d), a);
-    sbias[(size_t)(l * B + b) * 128 + h * 16 + j] = j < n_mem ? a * 0.125f : -1e30f;
+  if (threadIdx.x < XF_IB * 16) {
+    const int ib = threadIdx.x >> 4, j = threadIdx.x & 15;
+    if (b0 + ib < B) {
+      float a = 0.f;
+      for (int d = 0; d < 64; ++d) a = fmaf(sK[ib][j][d], __ldg(bq[l] + h * 64 + d), a);
+      sbias[(size_t)(l * B + b0 + ib) * 128 + h * 16 + j] = j < n_mem ? a * 0.125f : -1e30f;
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int n_mem, const float* const* __restrict__ wo,
+__global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int B, int n_mem, const float* const* __restrict__ wo,
                                                       bf16* __restrict__ Nt) {
-  __shared__ __align__(16) float sV[64][16];              // [d][j]: the 16 tokens of one d are one 64-byte row
+  __shared__ __align__(16) float sV[XF_IB][64][16];       // [image][d][j]: the 16 tokens of one d are one 64-byte row
   pdl_launch();
   pdl_wait();
-  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z, B = gridDim.x;
-  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-    const int j = i >> 6, d = i & 63;
-    sV[d][j] = j < n_mem ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
+  const int b0 = blockIdx.x * XF_IB, h = blockIdx.y, l = blockIdx.z;
+  for (int i = threadIdx.x; i < XF_IB * 16 * 64; i += blockDim.x) {
+    const int ib = i >> 10, j = (i >> 6) & 15, d = i & 63;
+    const int b = b0 + ib;
+    sV[ib][d][j] = (j < n_mem && b < B) ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
   }
   __syncthreads();
   const float* W = wo[l];                       // Dense kernel (in = h*64+d, out = f), row-major
   for (int f = threadIdx.x; f < 512; f += blockDim.x) {
-    float acc[16];
+#pragma unroll 1
+    for (int ip = 0; ip < XF_IB; ip += 2) {                  // two images per pass: 32 accumulators, weights re-read from L1
+      float acc[2][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
 #pragma unroll 4
-    for (int d = 0; d < 64; ++d) {
-      const float w = __ldg(W + (size_t)(h * 64 + d) * 512 + f);
+      for (int d = 0; d < 64; ++d) {
+        const float w = __ldg(W + (size_t)(h * 64 + d) * 512 + f);
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {                       // broadcast 16-byte shared loads
-        const float4 vq = *reinterpret_cast<const float4*>(&sV[d][j4 * 4]);
-        acc[4 * j4] = fmaf(vq.x, w, acc[4 * j4]);
-        acc[4 * j4 + 1] = fmaf(vq.y, w, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(vq.z, w, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(vq.w, w, acc[4 * j4 + 3]);
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {                   // broadcast 16-byte shared loads
+            const float4 vq = *reinterpret_cast<const float4*>(&sV[ip + q][d][j4 * 4]);
+            acc[q][4 * j4] = fmaf(vq.x, w, acc[q][4 * j4]);
+            acc[q][4 * j4 + 1] = fmaf(vq.y, w, acc[q][4 * j4 + 1]);
+            acc[q][4 * j4 + 2] = fmaf(vq.z, w, acc[q][4 * j4 + 2]);
+            acc[q][4 * j4 + 3] = fmaf(vq.w, w, acc[q][4 * j4 + 3]);
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int b = b0 + ip + q;
+        if (b < B) {
+          bf16* dst = Nt + ((size_t)(l * B + b) * 512 + f) * 128 + h * 16;
+          const float* c = acc[q];
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(c[0], c[1]), pack2(c[2], c[3]), pack2(c[4], c[5]), pack2(c[6], c[7]));
+          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack2(c[8], c[9]), pack2(c[10], c[11]), pack2(c[12], c[13]), pack2(c[14], c[15]));
+        }
       }
     }
-    bf16* dst = Nt + ((size_t)(l * B + b) * 512 + f) * 128 + h * 16;
-    uint4 o0 = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
-    uint4 o1 = make_uint4(pack2(acc[8], acc[9]), pack2(acc[10], acc[11]), pack2(acc[12], acc[13]), pack2(acc[14], acc[15]));
-    *reinterpret_cast<uint4*>(dst) = o0;
-    *reinterpret_cast<uint4*>(dst + 8) = o1;
   }
 }
 
@@ -427,8 +455,9 @@ int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const float* cons
     set_last_error("xattn_fold: at most 16 memory tokens, plain bf16 K/V");
     return 1;
   }
-  FPNMT_CUDA_OK(launch_k(k_xattn_fold_q, dim3(B, 8, L), dim3(256), 0, s, ckv, n_mem, wq, bq, Mt, sbias));
-  FPNMT_CUDA_OK(launch_k(k_xattn_fold_o, dim3(B, 8, L), dim3(256), 0, s, ckv, n_mem, wo, Nt));
+  const int gb = (B + XF_IB - 1) / XF_IB;
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_q, dim3(gb, 8, L), dim3(256), 0, s, ckv, B, n_mem, wq, bq, Mt, sbias));
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_o, dim3(gb, 8, L), dim3(256), 0, s, ckv, B, n_mem, wo, Nt));
   // A launch WITHOUT the programmatic-serialization attribute: it starts only after the fold kernels have completed
   // and been flushed, so later kernels (which prefetch Mt / Nt before their griddepcontrol.wait) can never overtake them.
   k_xattn_fence<<<1, 32, 0, s>>>();
