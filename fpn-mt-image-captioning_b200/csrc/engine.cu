@@ -882,21 +882,28 @@ int Engine::build_decoder() {
       xNt = (bf16*)dalloc((size_t)L * B * 512 * 128 * 2);
       xSb = (float*)dalloc((size_t)L * B * 128 * 4);
       if (!xMt || !xNt || !xSb) return FPNMT_ERR_CUDA;
-      std::vector<const float*> hq(L), hb(L), ho(L);
+      // bf16 copies of the projection weights for the mma.sync fold kernels: Wq as stored [k][(h,d)], Wo transposed [f][(h,d)]
+      std::vector<uint16_t> hwq((size_t)L * 512 * 512), hwo((size_t)L * 512 * 512);
+      std::vector<const float*> hb(L);
       for (int l = 0; l < L; ++l) {
         const std::string m = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l) + "/mha2";
-        float *a, *b2, *c;
-        RC(prep_vec(m + "/wq/kernel", &a));
+        const HostW *kq = W(m + "/wq/kernel"), *ko = W(m + "/dense/kernel");
+        if (!kq || !ko) return FPNMT_ERR_MISSING;
+        if (kq->data.size() != 512 * 512 || ko->data.size() != 512 * 512) return fail(FPNMT_ERR_INVALID, m + ": projection kernels must be 512x512");
+        for (size_t i = 0; i < 512 * 512; ++i) hwq[(size_t)l * 512 * 512 + i] = f2bf(kq->data[i]);
+        for (int hd = 0; hd < 512; ++hd)
+          for (int f = 0; f < 512; ++f) hwo[((size_t)l * 512 + f) * 512 + hd] = f2bf(ko->data[(size_t)hd * 512 + f]);
+        float* b2;
         RC(prep_vec(m + "/wq/bias", &b2));
-        RC(prep_vec(m + "/dense/kernel", &c));
-        hq[l] = a; hb[l] = b2; ho[l] = c;
+        hb[l] = b2;
       }
-      const float** dq = (const float**)dalloc(L * sizeof(float*));
+      bf16* dq = (bf16*)dalloc(hwq.size() * 2);
+      bf16* d_o = (bf16*)dalloc(hwo.size() * 2);
       const float** db = (const float**)dalloc(L * sizeof(float*));
-      const float** d_o = (const float**)dalloc(L * sizeof(float*));
-      FPNMT_CUDA_OK(cudaMemcpy(dq, hq.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
+      if (!dq || !d_o || !db) return FPNMT_ERR_CUDA;
+      FPNMT_CUDA_OK(cudaMemcpy(dq, hwq.data(), hwq.size() * 2, cudaMemcpyHostToDevice));
+      FPNMT_CUDA_OK(cudaMemcpy(d_o, hwo.data(), hwo.size() * 2, cudaMemcpyHostToDevice));
       FPNMT_CUDA_OK(cudaMemcpy(db, hb.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
-      FPNMT_CUDA_OK(cudaMemcpy(d_o, ho.data(), L * sizeof(float*), cudaMemcpyHostToDevice));
       Act ca = ckv.a;
       const int nm = n_base_;
       Op o = ew_op("xattn_fold", [=](cudaStream_t s) { return launch_xattn_fold(ca, B, nm, L, dq, db, d_o, xMt, xNt, xSb, s); },

@@ -341,123 +341,112 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int Btot, 
 
 // ------------------------------------------------------------------------------------------------ folding kernels
 // grid (B, heads = 8, L), 256 threads.  Keys/values of one (image, head, layer) are staged in shared memory as fp32.
-// Both fold kernels process XF_IB images per block so that the 128 KB weight slice of a (layer, head) leaves L2 once per
-// XF_IB images (with one image per block the kernels moved 0.4-0.8 GB through L2 and took 209 + 156 us per batch).
-constexpr int XF_IB = 4;
+// Fold kernels on mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  The per-(layer, image, head) products have M or N = 16
+// (the memory tokens), far below tcgen05's 128-row tiles, and run once per batch (3.2 GFLOP):
+//   fold_q:  Mt_b,h[16 j][512 k]  = K_b,h[16 j][64 d] . Wq_h[512 k][64 d]^T / 8      (A = K, B = Wq rows, "col" operand)
+//   fold_o:  Nt_b,h[512 f][16 j]  = WoT_h[512 f][64 d] . V_b,h[16 j][64 d]^T          (A = WoT rows, B = V rows)
+// Fragments are read straight from global memory in the m16n8k16 register layout (4-byte loads of bf16 pairs); block =
+// one (image, head, layer), 4 warps, each warp owns 128 of the 512 k (fold_q) or f (fold_o).
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ld_pair_bf16(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
-__global__ void __launch_bounds__(256) k_xattn_fold_q(Act ckv, int B, int n_mem, const float* const* __restrict__ wq,
+__global__ void __launch_bounds__(128) k_xattn_fold_q(Act ckv, int B, int n_mem, const bf16* __restrict__ wq,
                                                       const float* const* __restrict__ bq, bf16* __restrict__ Mt,
                                                       float* __restrict__ sbias) {
-  __shared__ __align__(16) float sK[XF_IB][16][64];
   pdl_launch();
   pdl_wait();
-  const int b0 = blockIdx.x * XF_IB, h = blockIdx.y, l = blockIdx.z;
-  for (int i = threadIdx.x; i < XF_IB * 16 * 64; i += blockDim.x) {
-    const int ib = i >> 10, j = (i >> 6) & 15, d = i & 63;
-    const int b = b0 + ib;
-    sK[ib][j][d] = (j < n_mem && b < B) ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + h * 64 + d]) : 0.f;
+  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;            // fragment row / column pair of this lane
+  const bf16* Kb = ckv.p + (size_t)(b * n_mem) * ckv.ld + l * 1024 + h * 64;
+  // A fragments: K_b,h rows j = gr and gr + 8 (zero beyond n_mem), all four k-steps
+  uint32_t a[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int d0 = ks * 16 + gc;
+    a[ks][0] = gr < n_mem ? ld_pair_bf16(Kb + (size_t)gr * ckv.ld + d0) : 0u;
+    a[ks][1] = gr + 8 < n_mem ? ld_pair_bf16(Kb + (size_t)(gr + 8) * ckv.ld + d0) : 0u;
+    a[ks][2] = gr < n_mem ? ld_pair_bf16(Kb + (size_t)gr * ckv.ld + d0 + 8) : 0u;
+    a[ks][3] = gr + 8 < n_mem ? ld_pair_bf16(Kb + (size_t)(gr + 8) * ckv.ld + d0 + 8) : 0u;
   }
-  __syncthreads();
-  const float* W = wq[l];                       // Dense kernel (in = k, out = h*64+d), row-major
-  for (int k = threadIdx.x; k < 512; k += blockDim.x) {
-    float w[64];
+  const bf16* W = wq + (size_t)l * 512 * 512 + h * 64;      // [k][h*64 + d]
+  bf16* dst = Mt + ((size_t)(l * B + b) * 128 + h * 16) * 512;
+#pragma unroll 4
+  for (int nt = 0; nt < 16; ++nt) {
+    const int k0 = warp * 128 + nt * 8;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const bf16* wr = W + (size_t)(k0 + gr) * 512 + gc;      // B fragment: n = k0 + gr, k = d
 #pragma unroll
-    for (int d4 = 0; d4 < 16; ++d4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * 512 + h * 64 + d4 * 4));
-      w[4 * d4] = v.x; w[4 * d4 + 1] = v.y; w[4 * d4 + 2] = v.z; w[4 * d4 + 3] = v.w;
-    }
-    for (int ib = 0; ib < XF_IB; ++ib) {
-      if (b0 + ib >= B) break;
-      bf16* dst = Mt + ((size_t)(l * B + b0 + ib) * 128 + h * 16) * 512;
-#pragma unroll 1
-      for (int j0 = 0; j0 < 16; j0 += 4) {                   // four independent accumulation chains
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int d4 = 0; d4 < 16; ++d4) {
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {                   // broadcast 16-byte shared loads
-            const float4 kq = *reinterpret_cast<const float4*>(&sK[ib][j0 + jj][d4 * 4]);
-            a[jj] = fmaf(kq.x, w[4 * d4], a[jj]);
-            a[jj] = fmaf(kq.y, w[4 * d4 + 1], a[jj]);
-            a[jj] = fmaf(kq.z, w[4 * d4 + 2], a[jj]);
-            a[jj] = fmaf(kq.w, w[4 * d4 + 3], a[jj]);
-          }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) dst[(size_t)(j0 + jj) * 512 + k] = __float2bfloat16_rn(a[jj] * 0.125f);
-      }
-    }
+    for (int ks = 0; ks < 4; ++ks) mma16816(c, a[ks], ld_pair_bf16(wr + ks * 16), ld_pair_bf16(wr + ks * 16 + 8));
+    __nv_bfloat162 lo = __floats2bfloat162_rn(c[0] * 0.125f, c[1] * 0.125f), hi = __floats2bfloat162_rn(c[2] * 0.125f, c[3] * 0.125f);
+    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)gr * 512 + k0 + gc) = lo;
+    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)(gr + 8) * 512 + k0 + gc) = hi;
   }
-  if (threadIdx.x < XF_IB * 16) {
-    const int ib = threadIdx.x >> 4, j = threadIdx.x & 15;
-    if (b0 + ib < B) {
-      float a = 0.f;
-      for (int d = 0; d < 64; ++d) a = fmaf(sK[ib][j][d], __ldg(bq[l] + h * 64 + d), a);
-      sbias[(size_t)(l * B + b0 + ib) * 128 + h * 16 + j] = j < n_mem ? a * 0.125f : -1e30f;
-    }
+  if (threadIdx.x < 16) {                                    // score bias: bq . K / 8 (-1e30 masks the padded tokens)
+    const int j = threadIdx.x;
+    float acc = 0.f;
+    if (j < n_mem)
+      for (int d = 0; d < 64; ++d) acc = fmaf(__bfloat162float(Kb[(size_t)j * ckv.ld + d]), __ldg(bq[l] + h * 64 + d), acc);
+    sbias[(size_t)(l * B + b) * 128 + h * 16 + j] = j < n_mem ? acc * 0.125f : -1e30f;
   }
 }
 
-__global__ void __launch_bounds__(256) k_xattn_fold_o(Act ckv, int B, int n_mem, const float* const* __restrict__ wo,
+__global__ void __launch_bounds__(128) k_xattn_fold_o(Act ckv, int B, int n_mem, const bf16* __restrict__ woT,
                                                       bf16* __restrict__ Nt) {
-  __shared__ __align__(16) float sV[XF_IB][64][16];       // [image][d][j]: the 16 tokens of one d are one 64-byte row
   pdl_launch();
   pdl_wait();
-  const int b0 = blockIdx.x * XF_IB, h = blockIdx.y, l = blockIdx.z;
-  for (int i = threadIdx.x; i < XF_IB * 16 * 64; i += blockDim.x) {
-    const int ib = i >> 10, j = (i >> 6) & 15, d = i & 63;
-    const int b = b0 + ib;
-    sV[ib][d][j] = (j < n_mem && b < B) ? __bfloat162float(ckv.p[(size_t)(b * n_mem + j) * ckv.ld + l * 1024 + 512 + h * 64 + d]) : 0.f;
+  const int b = blockIdx.x, h = blockIdx.y, l = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const bf16* Vb = ckv.p + (size_t)(b * n_mem) * ckv.ld + l * 1024 + 512 + h * 64;
+  // B fragments: V_b,h as the "col" operand, n = token j, k = d; two n-tiles (j 0..7, 8..15), four k-steps
+  uint32_t bv[2][4][2];
+#pragma unroll
+  for (int n8 = 0; n8 < 2; ++n8) {
+    const int j = n8 * 8 + gr;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      bv[n8][ks][0] = j < n_mem ? ld_pair_bf16(Vb + (size_t)j * ckv.ld + ks * 16 + gc) : 0u;
+      bv[n8][ks][1] = j < n_mem ? ld_pair_bf16(Vb + (size_t)j * ckv.ld + ks * 16 + gc + 8) : 0u;
+    }
   }
-  __syncthreads();
-  const float* W = wo[l];                       // Dense kernel (in = h*64+d, out = f), row-major
-  for (int f = threadIdx.x; f < 512; f += blockDim.x) {
-#pragma unroll 1
-    for (int ip = 0; ip < XF_IB; ip += 2) {                  // two images per pass: 32 accumulators, weights re-read from L1
-      float acc[2][16];
+  const bf16* W = woT + (size_t)l * 512 * 512 + h * 64;     // [f][h*64 + d]
+#pragma unroll 2
+  for (int mt = 0; mt < 8; ++mt) {
+    const int f0 = warp * 128 + mt * 16;
+    float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const bf16* w0 = W + (size_t)(f0 + gr) * 512 + gc;
+    const bf16* w1 = w0 + 8 * 512;
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4] = {ld_pair_bf16(w0 + ks * 16), ld_pair_bf16(w1 + ks * 16), ld_pair_bf16(w0 + ks * 16 + 8), ld_pair_bf16(w1 + ks * 16 + 8)};
+      mma16816(c[0], a, bv[0][ks][0], bv[0][ks][1]);
+      mma16816(c[1], a, bv[1][ks][0], bv[1][ks][1]);
+    }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
-#pragma unroll 4
-      for (int d = 0; d < 64; ++d) {
-        const float w = __ldg(W + (size_t)(h * 64 + d) * 512 + f);
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {                   // broadcast 16-byte shared loads
-            const float4 vq = *reinterpret_cast<const float4*>(&sV[ip + q][d][j4 * 4]);
-            acc[q][4 * j4] = fmaf(vq.x, w, acc[q][4 * j4]);
-            acc[q][4 * j4 + 1] = fmaf(vq.y, w, acc[q][4 * j4 + 1]);
-            acc[q][4 * j4 + 2] = fmaf(vq.z, w, acc[q][4 * j4 + 2]);
-            acc[q][4 * j4 + 3] = fmaf(vq.w, w, acc[q][4 * j4 + 3]);
-          }
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int b = b0 + ip + q;
-        if (b < B) {
-          bf16* dst = Nt + ((size_t)(l * B + b) * 512 + f) * 128 + h * 16;
-          const float* c = acc[q];
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(c[0], c[1]), pack2(c[2], c[3]), pack2(c[4], c[5]), pack2(c[6], c[7]));
-          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack2(c[8], c[9]), pack2(c[10], c[11]), pack2(c[12], c[13]), pack2(c[14], c[15]));
-        }
-      }
+    for (int n8 = 0; n8 < 2; ++n8) {
+      bf16* d0 = Nt + ((size_t)(l * B + b) * 512 + f0 + gr) * 128 + h * 16 + n8 * 8 + gc;
+      *reinterpret_cast<__nv_bfloat162*>(d0) = __floats2bfloat162_rn(c[n8][0], c[n8][1]);
+      *reinterpret_cast<__nv_bfloat162*>(d0 + 8 * 128) = __floats2bfloat162_rn(c[n8][2], c[n8][3]);
     }
   }
 }
 
 __global__ void k_xattn_fence() {}
 
-int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const float* const* wq, const float* const* bq,
-                      const float* const* wo, bf16* Mt, bf16* Nt, float* sbias, cudaStream_t s) {
+int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const bf16* wq, const float* const* bq, const bf16* woT,
+                      bf16* Mt, bf16* Nt, float* sbias, cudaStream_t s) {
   if (n_mem > 16 || ckv.lo) {
     set_last_error("xattn_fold: at most 16 memory tokens, plain bf16 K/V");
     return 1;
   }
-  const int gb = (B + XF_IB - 1) / XF_IB;
-  FPNMT_CUDA_OK(launch_k(k_xattn_fold_q, dim3(gb, 8, L), dim3(256), 0, s, ckv, B, n_mem, wq, bq, Mt, sbias));
-  FPNMT_CUDA_OK(launch_k(k_xattn_fold_o, dim3(gb, 8, L), dim3(256), 0, s, ckv, B, n_mem, wo, Nt));
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_q, dim3(B, 8, L), dim3(128), 0, s, ckv, B, n_mem, wq, bq, Mt, sbias));
+  FPNMT_CUDA_OK(launch_k(k_xattn_fold_o, dim3(B, 8, L), dim3(128), 0, s, ckv, B, n_mem, woT, Nt));
   // A launch WITHOUT the programmatic-serialization attribute: it starts only after the fold kernels have completed
   // and been flushed, so later kernels (which prefetch Mt / Nt before their griddepcontrol.wait) can never overtake them.
   k_xattn_fence<<<1, 32, 0, s>>>();

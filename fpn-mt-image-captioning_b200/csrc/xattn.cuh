@@ -47,7 +47,9 @@ int make_xattn_op(XattnOp* op, const bf16* Mt, const bf16* Nt, int L, int Btot, 
                   const float* sbias, const float* obias, const float* gamma, const float* beta, const Act& x, const Act& out);
 
 // Folding kernels (once per batch, all layers): ckv = cross K/V activations [B*n_mem][L*2*512] (K at l*1024, V at +512).
-int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const float* const* wq, const float* const* bq,
-                      const float* const* wo, bf16* Mt, bf16* Nt, float* sbias, cudaStream_t s);
+// wq: bf16 [L][512 k][512 (h,d)] (the Dense kernel of mha2/wq as stored, in -> out); woT: bf16 [L][512 f][512 (h,d)] (the
+// mha2 output Dense kernel TRANSPOSED); bq: per-layer fp32 bias pointers.
+int launch_xattn_fold(const Act& ckv, int B, int n_mem, int L, const bf16* wq, const float* const* bq, const bf16* woT,
+                      bf16* Mt, bf16* Nt, float* sbias, cudaStream_t s);
 
 }  // namespace fpnmt
