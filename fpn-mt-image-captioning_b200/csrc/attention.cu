@@ -136,12 +136,22 @@ constexpr int EA_TILE = 64;                       // keys per tile
 constexpr int EA_TILE_BYTES = EA_TILE * DH * 2;   // 8 KB
 constexpr int EA_SMEM = EA_WARPS * 2 * EA_TILE_BYTES + EA_WARPS * 16 * 2 * 4;
 
-__global__ void __launch_bounds__(EA_WARPS * 32) k_enc_attention_mma(Act q, int q_col, Act kv, int k_col, int v_col, int Tq,
-                                                                    int Tk, Act out, int out_col) {
+// blockIdx.z selects the pyramid view: all (up to 4) cross-level attentions of an encoder layer run as ONE launch, the
+// long view first (z = 0), so the short ones fill the tail instead of paying a launch each.
+struct EncAttViews {
+  Act kv[4];
+  int Tk[4];
+  int col[4];      // query / output column block of the view
+};
+__global__ void __launch_bounds__(EA_WARPS * 32) k_enc_attention_mma(Act q, EncAttViews views, int k_col, int v_col, int Tq,
+                                                                    Act out) {
   extern __shared__ __align__(128) uint8_t ea_smem[];
   pdl_launch();
   pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y;
+  const Act kv = views.kv[blockIdx.z];
+  const int Tk = views.Tk[blockIdx.z];
+  const int q_col = views.col[blockIdx.z], out_col = q_col;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   uint8_t* sK = ea_smem + warp * 2 * EA_TILE_BYTES;
@@ -321,12 +331,47 @@ int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, 
       FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
       attr_done = true;
     }
-    FPNMT_CUDA_OK(launch_k(k_enc_attention_mma, dim3(grid), dim3(EA_WARPS * 32), (size_t)EA_SMEM, s, q, q_col, kv, k_col, v_col,
-                           Tq, Tk, out, out_col));
+    if (q_col != out_col) {
+      set_last_error("enc_attention: the tensor-core path writes the output at the query's column block");
+      return 1;
+    }
+    EncAttViews views{};
+    views.kv[0] = kv;
+    views.Tk[0] = Tk;
+    views.col[0] = q_col;
+    FPNMT_CUDA_OK(launch_k(k_enc_attention_mma, dim3(grid), dim3(EA_WARPS * 32), (size_t)EA_SMEM, s, q, views, k_col, v_col, Tq, out));
     return 0;
   }
   FPNMT_CUDA_OK(launch_k(k_enc_attention, dim3(grid), dim3(128), 0, s, q, q_col, kv, k_col, v_col, Tq, Tk, out, out_col));
   LAUNCH_CHECK();
+  return 0;
+}
+
+// All views of one encoder layer in a single launch (bf16 tensor-core path only; view v reads the query columns
+// [col[v], col[v]+heads*64) and writes its output there).
+int launch_enc_attention_views(Act q, const Act* kvs, const int* tks, const int* cols, int nviews, int k_col, int v_col, int B,
+                               int Tq, int heads, Act out, cudaStream_t s) {
+  if (Tq > 16 || nviews < 1 || nviews > 4 || q.lo || out.lo) {
+    set_last_error("enc_attention_views: Tq <= 16, 1..4 views, plain bf16 activations");
+    return 1;
+  }
+  EncAttViews views{};
+  for (int v = 0; v < nviews; ++v) {
+    if (kvs[v].lo) {
+      set_last_error("enc_attention_views: plain bf16 K/V");
+      return 1;
+    }
+    views.kv[v] = kvs[v];
+    views.Tk[v] = tks[v];
+    views.col[v] = cols[v];
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+    attr_done = true;
+  }
+  FPNMT_CUDA_OK(launch_k(k_enc_attention_mma, dim3(B, heads, nviews), dim3(EA_WARPS * 32), (size_t)EA_SMEM, s, q, views, k_col, v_col,
+                         Tq, out));
   return 0;
 }
 

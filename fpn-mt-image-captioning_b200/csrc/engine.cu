@@ -772,6 +772,25 @@ int Engine::build_mt_encoder(Program& p) {
     RC(prep_dense_cat({e + "/ffn2"}, &g2));
     Tensor q = rows_act(R, 4 * D), att = rows_act(R, 4 * D);
     RC(add_conv(p, ln + "_q", base, gq, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, q));
+    const char* force_simt = getenv("FPNMT_ENC_ATT_SIMT");
+    if (!split_ && !(force_simt && force_simt[0] == '1')) {
+      // bf16 mode: the four cross-level attentions of the layer as one launch (long view first)
+      struct V4 { Act kv[4]; int tk[4]; int col[4]; } v4;
+      double bytes = 0, flops = 0;
+      for (int v = 0; v < 4; ++v) {
+        v4.kv[v] = kv[v].a;
+        v4.tk[v] = ntok[v];
+        v4.col[v] = v * D;
+        bytes += (double)B * ntok[v] * 2 * D * 2;
+        flops += 4.0 * B * n_base_ * ntok[v] * D;
+      }
+      Act qa = q.a, oa = att.a;
+      const int tq = n_base_, kc = l * 2 * D, vc = l * 2 * D + D;
+      Op o = ew_op(ln + "_attn_views", [=](cudaStream_t s) { return launch_enc_attention_views(qa, v4.kv, v4.tk, v4.col, 4, kc, vc, B, tq, H, oa, s); },
+                   bytes, "attention");
+      o.flops = flops;
+      p.push_back(std::move(o));
+    } else {
     for (int v = 0; v < 4; ++v) {
       Act qa = q.a, ka = kv[v].a, oa = att.a;
       const int tk = ntok[v], tq = n_base_, kc = l * 2 * D, vc = l * 2 * D + D, qc = v * D;
@@ -780,6 +799,7 @@ int Engine::build_mt_encoder(Program& p) {
                    (double)B * tk * 2 * D * 2, "attention");
       o.flops = 4.0 * B * tq * tk * D;
       p.push_back(std::move(o));
+    }
     }
     float* y = (float*)dalloc((size_t)R * D * 4);
     Tensor none;

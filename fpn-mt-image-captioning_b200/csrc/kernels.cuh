@@ -42,6 +42,10 @@ int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s);
 // Encoder cross-level attention for one (layer, view): q (B*16 rows) vs K/V of a static view (B*Tk rows).
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
                          int out_col, cudaStream_t s);
+// All (<= 4) cross-level attentions of one encoder layer as ONE launch (bf16 mode): view v uses K/V tensor kvs[v] with tks[v]
+// keys and the query / output column block cols[v].
+int launch_enc_attention_views(Act q, const Act* kvs, const int* tks, const int* cols, int nviews, int k_col, int v_col, int B,
+                               int Tq, int heads, Act out, cudaStream_t s);
 // Decoder self-attention, one new position per row, KV cache with beam-ancestry indirection.
 // qkv: [rows][3*d] (q|k|v) of the new position; caches [rows][T][d]; anc [2][..][T] physical row per position, the two
 // step parities `anc_stride` ints apart (rows may be a slice of a larger batch: anc_stride = total rows * T).
