@@ -801,27 +801,32 @@ int Engine::build_mt_encoder(Program& p) {
       p.push_back(std::move(o));
     }
     }
-    float* y = (float*)dalloc((size_t)R * D * 4);
     Tensor none;
-    RC(add_conv(p, ln + "_out+res", att, go, 1, 1, 0, 0, ACT_NONE, RES_SAME, &base, none, y, D));
     float *g1p, *b1p, *g2p, *b2p;
     RC(prep_vec(e + "/layernorm1/gamma", &g1p));
     RC(prep_vec(e + "/layernorm1/beta", &b1p));
     RC(prep_vec(e + "/layernorm2/gamma", &g2p));
     RC(prep_vec(e + "/layernorm2/beta", &b2p));
-    Tensor out1 = rows_act(R, D);
-    {
-      Act oa = out1.a;
-      p.push_back(ew_op(ln + "_ln1", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g1p, b1p, 1e-6f, oa, s); }, (double)R * D * 6));
-    }
-    Tensor hdn = rows_act(R, FF);
-    RC(add_conv(p, ln + "_ffn1", out1, g1, 1, 1, 0, 0, ACT_LEAKY, RES_NONE, nullptr, hdn));
-    float* y2 = (float*)dalloc((size_t)R * D * 4);
-    RC(add_conv(p, ln + "_ffn2+res", hdn, g2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out1, none, y2, D));
-    Tensor out2 = rows_act(R, D);
-    {
-      Act oa = out2.a;
-      p.push_back(ew_op(ln + "_ln2", [=](cudaStream_t s) { return launch_layernorm_rows(y2, R, D, g2p, b2p, 1e-6f, oa, s); }, (double)R * D * 6));
+    Tensor out1 = rows_act(R, D), hdn = rows_act(R, FF), out2 = rows_act(R, D);
+    if (use_tgemm_) {
+      // skinny-row tgemm (R = 16 B rows): residual + LayerNorm fused into the epilogue, as in the decoder step
+      RC(add_dense(p, ln + "_out+res+ln", att, go, ACT_NONE, &base, out1, nullptr, 0, g1p, b1p));
+      RC(add_dense(p, ln + "_ffn1", out1, g1, ACT_LEAKY, nullptr, hdn));
+      RC(add_dense(p, ln + "_ffn2+res+ln", hdn, g2, ACT_NONE, &out1, out2, nullptr, 0, g2p, b2p));
+    } else {
+      float* y = (float*)dalloc((size_t)R * D * 4);
+      RC(add_conv(p, ln + "_out+res", att, go, 1, 1, 0, 0, ACT_NONE, RES_SAME, &base, none, y, D));
+      {
+        Act oa = out1.a;
+        p.push_back(ew_op(ln + "_ln1", [=](cudaStream_t s) { return launch_layernorm_rows(y, R, D, g1p, b1p, 1e-6f, oa, s); }, (double)R * D * 6));
+      }
+      RC(add_conv(p, ln + "_ffn1", out1, g1, 1, 1, 0, 0, ACT_LEAKY, RES_NONE, nullptr, hdn));
+      float* y2 = (float*)dalloc((size_t)R * D * 4);
+      RC(add_conv(p, ln + "_ffn2+res", hdn, g2, 1, 1, 0, 0, ACT_NONE, RES_SAME, &out1, none, y2, D));
+      {
+        Act oa = out2.a;
+        p.push_back(ew_op(ln + "_ln2", [=](cudaStream_t s) { return launch_layernorm_rows(y2, R, D, g2p, b2p, 1e-6f, oa, s); }, (double)R * D * 6));
+      }
     }
     base = out2;
     taps_["enc_layer" + std::to_string(l)] = out2;
