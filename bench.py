@@ -28,8 +28,12 @@ import argparse
 import json
 import os
 
-# stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
+# stdout carries exactly one JSON line.  NCCL logs through NCCL_DEBUG_FILE, except the NCCL_DEBUG=VERSION banner, which is a
+# bare printf to stdout: that level is mapped to WARN and the version is written to stderr by run_own instead.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_NCCL_BANNER = os.environ.get("NCCL_DEBUG", "").upper() == "VERSION"
+if _NCCL_BANNER:
+    os.environ["NCCL_DEBUG"] = "WARN"
 import subprocess
 import sys
 import threading
@@ -198,6 +202,8 @@ def run_own(args, wl):
     from fpnmt.weights import init_weights
 
     rank, local, world = fd.init_from_env("nccl")
+    if _NCCL_BANNER and rank == 0 and world > 1:
+        sys.stderr.write("NCCL version %s\n" % ".".join(str(v) for v in torch.cuda.nccl.version()))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, N, V, T = wl["batch"], wl["beam"], wl["vocab"], wl["max_len"]
