@@ -422,3 +422,33 @@ def test_true_beam_extension_matches_oracle():
     # the extension is not a no-op: a real beam may (and here does, for at least one image or step) leave the greedy path,
     # and its final score is never worse; identical output is also legal, so only the shapes are asserted unconditionally
     assert ids.shape == greedy_ids.shape
+
+
+def test_c2_full_size_properties():
+    """BASELINE config C2 at FULL size (ResNet-50-FPN, batch 64, beam 8, V = 10 000, T = 64, 6 layers, 512x512, the bench's
+    weight factory): size-independent properties - repeated runs bit-identical, captions follow their images under a batch
+    permutation, the streaming (double-buffered) call equals the one-shot call, and a 4-image engine built from the same
+    weights reproduces the first images of the 64-image batch (batch-size invariance of every kernel's tiling)."""
+    from fpnmt.engine import Engine
+    from fpnmt.weights import init_weights
+    bb, Bf, Nf, Vf, Tf = "resnet50", 64, 8, 10000, 64
+    w = init_weights(bb, vocab=Vf, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    imgs = (torch.rand(Bf, 512, 512, 3, generator=g) * 2 - 1)
+    eng = Engine(w, backbone=bb, batch=Bf, beam=Nf, vocab=Vf, max_len=Tf, use_graphs=True)
+    dev = imgs.cuda()
+    ids1, len1 = eng.generate(dev, early_stop=False)
+    ids1b, len1b = eng.generate(dev, early_stop=False)
+    assert torch.equal(ids1, ids1b) and torch.equal(len1, len1b)
+    assert tuple(ids1.shape) == (Bf, Tf) and int(len1.min()) == Tf and int(ids1.max()) < Vf and int(ids1.min()) >= 0
+    perm = torch.randperm(Bf, generator=torch.Generator().manual_seed(5))
+    ids2, len2 = eng.generate(imgs[perm].cuda(), early_stop=False)
+    assert torch.equal(ids1[perm], ids2) and torch.equal(len1[perm], len2)
+    pinned = [imgs.pin_memory(), imgs[perm].contiguous().pin_memory()]
+    outs = list(eng.generate_stream(iter(pinned), early_stop=False))
+    assert torch.equal(outs[0][0], ids1) and torch.equal(outs[1][0], ids2)
+    eng.close()
+    small = Engine(w, backbone=bb, batch=4, beam=Nf, vocab=Vf, max_len=Tf, use_graphs=True)
+    ids4, len4 = small.generate(imgs[:4].cuda(), early_stop=False)
+    small.close()
+    assert torch.equal(ids4, ids1[:4]) and torch.equal(len4, len1[:4])
