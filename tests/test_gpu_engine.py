@@ -452,3 +452,30 @@ def test_c2_full_size_properties():
     ids4, len4 = small.generate(imgs[:4].cuda(), early_stop=False)
     small.close()
     assert torch.equal(ids4, ids1[:4]) and torch.equal(len4, len1[:4])
+
+
+def test_full_depth_resnet50_512_parity_bf16x3():
+    """The reference's own depth and resolution (ResNet-50-FPN, 512x512, 6 encoder + 6 decoder layers) in the parity
+    mode: encoder memory within 3e-3 rel-L2 of the oracle, teacher-forced per-step log-probs within the north-star 2e-3
+    absolute, arg-max identical, generated ids identical to the oracle's cached decode."""
+    from fpnmt.engine import Engine
+    bb, Lf, Vf, Tf, Nf = "resnet50", 6, 1000, 8, 4
+    w = small_weights(bb, Vf, Lf, seed=3)
+    Wv = O.W(w)
+    img = O.test_images(1, 512, seed=21)
+    with torch.no_grad():
+        mem_ref = O.encoder(img, Wv, bb, num_layers=Lf, input_vocab_size=1024)
+    eng = Engine(w, backbone=bb, batch=1, beam=Nf, vocab=Vf, max_len=Tf, num_layers=Lf, image_size=512, precision="bf16x3")
+    mem = eng.encode(img.cuda()).cpu()
+    assert rel(mem, mem_ref) < 3e-3
+    gtok = torch.randint(4, Vf, (1, Tf), generator=torch.Generator().manual_seed(8))
+    gtok[:, 0] = 2
+    lg = eng.decode_logits(mem_ref.cuda(), gtok.int().cuda()).cpu()
+    ref_lg, _ = O.transformer_logits(mem_ref, gtok, Wv, O.create_look_ahead_mask(Tf), Tf, num_layers=Lf)
+    lp, lpr = torch.log_softmax(lg, -1), torch.log_softmax(ref_lg, -1)
+    assert float((lp - lpr).abs().max()) < 2e-3
+    assert bool((lp.argmax(-1) == lpr.argmax(-1)).all())
+    ids, lens = eng.generate(img.cuda(), early_stop=True)
+    ref_ids, ref_len = O.predict_batch_cached(mem_ref, Wv, Tf, Nf, 2, 3, num_layers=Lf)
+    eng.close()
+    assert (ids.numpy() == ref_ids).all() and (lens.numpy() == ref_len).all()
