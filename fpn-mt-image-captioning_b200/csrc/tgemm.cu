@@ -12,7 +12,8 @@
 namespace fpnmt {
 
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;          // 16 KB
-constexpr int TG_LN_STRIDE = 129;                      // floats per row of the transposed LN scratch (bank-conflict free)
+constexpr int TG_LN_STRIDE = 132;                      // floats per row of the transposed scratch: 16-byte aligned rows with a
+                                                       // 4-bank skew (feature-major writes and float4 row reads both conflict-free)
 constexpr int TG_LN_BYTES = 32 * TG_LN_STRIDE * 4 + 128;
 
 size_t tgemm_smem_bytes(int BN) {
@@ -313,7 +314,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float x[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = sLN[lane * TG_LN_STRIDE + e * 32 + i];
+        for (int i = 0; i < 8; ++i) {
+          const float4 q4 = *reinterpret_cast<const float4*>(sLN + lane * TG_LN_STRIDE + e * 32 + i * 4);
+          x[4 * i] = q4.x; x[4 * i + 1] = q4.y; x[4 * i + 2] = q4.z; x[4 * i + 3] = q4.w;
+        }
         if (p.ksplit == 2) {                 // split-K: add the partial sums of the CTA that owns the other K half
           cluster_sync_all();                // #0: both halves' partial tiles are in their shared-memory scratch
           if (ks == 0) {
@@ -398,7 +402,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           cluster_sync_all();                                  // #1: every CTA's row statistics are published
           const float2 s0 = ld_dsmem_f2(&sStat[lane], 0), s1 = ld_dsmem_f2(&sStat[lane], 1), s2 = ld_dsmem_f2(&sStat[lane], 2),
                        s3 = ld_dsmem_f2(&sStat[lane], 3);
-          cluster_sync_all();                                  // #2: nobody exits while its statistics are still being read
           const float mean = 0.25f * (s0.x + s1.x + s2.x + s3.x);
           const float e0 = s0.x - mean, e1 = s1.x - mean, e2 = s2.x - mean, e3 = s3.x - mean;
           const float M2 = s0.y + s1.y + s2.y + s3.y + 128.f * (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
@@ -418,6 +421,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
               st_act8(p.out, (size_t)row, fo + g * 8, o);
             }
           }
+          cluster_sync_all();                                  // #2: nobody exits while its statistics are still being read
+                                                               //     (after the stores: off the critical path of the output)
         }
         if (e == 0 && lane == 0 && rt == rt0) DBG(6 + ch);
         if (CHUNKS > 1 || rt + 1 < rt1) asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch is reused
