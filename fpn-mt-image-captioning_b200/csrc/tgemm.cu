@@ -171,7 +171,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (uniform) loop and waits on the barriers; one elected lane issues (see umma_bf16_pred).
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
       int gA = 0, gB = 0, acc = 0;
       uint32_t acc_phase = 0;
       for (int rt = rt0; rt < rt1; ++rt) {
@@ -191,8 +193,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           mbar_wait(&fullB[sb], (gB / NG) & 1);
           ++gB;
           tc_fence_after();
-          if (g == 0 && rt == rt0) DBG(3);
-          if (g == 0 && rt > rt0 && rt - rt0 <= 4) DBG(8 + (rt - rt0));
+          if (g == 0 && rt == rt0 && leader) DBG(3);
+          if (g == 0 && rt > rt0 && rt - rt0 <= 4 && leader) DBG(8 + (rt - rt0));
           const int n = min(G, kiters - (g_begin + g) * G);
           const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA + sa * G * TG_A_BYTES));
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB + sb * G * B_BYTES));
@@ -201,20 +203,20 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
             for (int i = 0; i < G; ++i)
 #pragma unroll
               for (int k = 0; k < TG_BK / 16; ++k)
-                umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
-                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_pred(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
+                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u, leader);
           } else {
             for (int i = 0; i < n; ++i)
 #pragma unroll
               for (int k = 0; k < TG_BK / 16; ++k)
-                umma_bf16(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
-                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_pred(d_tmem, adesc0 + (uint64_t)(i * (TG_A_BYTES >> 4) + 2 * k), bdesc0 + (uint64_t)(i * (B_BYTES >> 4) + 2 * k),
+                          IDESC, (g > 0 || i > 0 || k > 0) ? 1u : 0u, leader);
           }
-          umma_commit(&emptyB[sb]);
-          if (!p.stationary) umma_commit(&emptyA[sa]);
+          umma_commit_pred(&emptyB[sb], leader);
+          if (!p.stationary) umma_commit_pred(&emptyA[sa], leader);
         }
-        umma_commit(&tfull[acc]);
-        if (rt == rt0) DBG(4);
+        umma_commit_pred(&tfull[acc], leader);
+        if (rt == rt0 && leader) DBG(4);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
