@@ -252,6 +252,29 @@ __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t pred) {
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(pred)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pred(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::"r"(
+          smem_u32(smem)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pred(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                 uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n" ::"r"(
+          smem_u32(smem)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_pred(uint64_t* bar, uint32_t bytes, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

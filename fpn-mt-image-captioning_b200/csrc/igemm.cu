@@ -118,7 +118,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && (int)blockIdx.x < total_tiles) {
+    // Convergent warp: all lanes run the (uniform) loops and barrier waits, one elected lane issues.  Inside an
+    // `if (lane == 0)` region ptxas wraps every UTMALDG / UTCHMMA in an ELECT / R2UR retry loop (see umma_bf16_pred).
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    if ((int)blockIdx.x < total_tiles) {
       // weights of the first ring pass of the first tile: static data, fetched before the grid dependency resolves
       const int npre = kiters < STAGES ? kiters : STAGES;
       {
@@ -128,12 +131,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           const int t = (it / p.kchunks) % taps;
           const int term = it / (p.kchunks * taps);
           const int bko = (term == 1) ? p.b_lo_off : 0;
-          mbar_expect_tx(&full_bar[it], A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(sB + it * B_STAGE_BYTES, &tmB, &full_bar[it], bko + t * p.Cin + kc * IG_BK, co_t * BN);
+          mbar_expect_tx_pred(&full_bar[it], A_STAGE_BYTES + B_STAGE_BYTES, leader);
+          tma_load_2d_pred(sB + it * B_STAGE_BYTES, &tmB, &full_bar[it], bko + t * p.Cin + kc * IG_BK, co_t * BN, leader);
         }
       }
       pdl_wait();
-      DBG(2);
+      if (leader) DBG(2);
       int git = 0;   // k-iterations issued so far by this CTA
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int co_t = tile % p.tiles_co;
@@ -153,10 +156,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const int stage = git % STAGES;
               if (git >= npre) {
                 mbar_wait(&empty_bar[stage], ((git / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK, co_t * BN);
+                mbar_expect_tx_pred(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES, leader);
+                tma_load_2d_pred(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK, co_t * BN, leader);
               }
-              tma_load_4d(sA + stage * A_STAGE_BYTES, ma, &full_bar[stage], kc * IG_BK, x0 + dx, y0 + dy, n0);
+              tma_load_4d_pred(sA + stage * A_STAGE_BYTES, ma, &full_bar[stage], kc * IG_BK, x0 + dx, y0 + dy, n0, leader);
             }
           }
         }
@@ -164,7 +167,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -176,22 +180,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (it == 0) DBG(3);
+          if (it == 0 && leader) DBG(3);
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {
             // +32 bytes (2 x 16 B units) per UMMA_K = 16 bf16 inside the 128 B swizzle atom
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_pred(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u, leader);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+          umma_commit_pred(&empty_bar[stage], leader);   // frees the smem stage when these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        DBG(4);
-        umma_commit(&tfull_bar[acc]);       // accumulator ready for the epilogue
+        if (leader) DBG(4);
+        umma_commit_pred(&tfull_bar[acc], leader);       // accumulator ready for the epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

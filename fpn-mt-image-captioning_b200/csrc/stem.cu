@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
 
   if (warp == 4) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_expect_tx(fullW, C::KCH * C::W_CHUNK);
-      for (int c = 0; c < C::KCH; ++c) tma_load_2d(sW + c * C::W_CHUNK, &tmW, fullW, c * 64, 0);
+    // convergent warp, one elected lane issues (see umma_bf16_pred in common.cuh)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
+      mbar_expect_tx_pred(fullW, C::KCH * C::W_CHUNK, leader);
+      for (int c = 0; c < C::KCH; ++c) tma_load_2d_pred(sW + c * C::W_CHUNK, &tmW, fullW, c * 64, 0, leader);
       mbar_wait(fullW, 0);
       constexpr uint32_t IDESC = umma_idesc_bf16(128, COUT);
       const uint64_t w0 = umma_desc_sw128(smem_u32(sW));
@@ -121,17 +123,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
         mbar_wait(&tempty[b], ph ^ 1);
         mbar_wait(&fullA[b], ph);
         tc_fence_after();
-        SDBG(7);
+        if (leader) SDBG(7);
         const uint64_t a0 = umma_desc_sw128(smem_u32(sA + b * C::KCH * ST_A_CHUNK));
 #pragma unroll
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
           const int c = ks >> 2, k = ks & 3;
-          umma_bf16(tmem_base + b * COUT, a0 + (uint64_t)(c * (ST_A_CHUNK >> 4) + 2 * k),
-                    w0 + (uint64_t)(c * (C::W_CHUNK >> 4) + 2 * k), IDESC, ks > 0 ? 1u : 0u);
+          umma_bf16_pred(tmem_base + b * COUT, a0 + (uint64_t)(c * (ST_A_CHUNK >> 4) + 2 * k),
+                    w0 + (uint64_t)(c * (C::W_CHUNK >> 4) + 2 * k), IDESC, ks > 0 ? 1u : 0u, leader);
         }
-        umma_commit(&emptyA[b]);
-        umma_commit(&tfull[b]);
-        SDBG(8);
+        umma_commit_pred(&emptyA[b], leader);
+        umma_commit_pred(&tfull[b], leader);
+        if (leader) SDBG(8);
       }
     }
     __syncwarp();

@@ -126,20 +126,22 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
   const bool helper_b = false;   // measured slower on B200 (qkv 6.7 -> 7.6 us): a second issuing thread does not help
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // convergent warp, one elected lane issues (see umma_bf16_pred in common.cuh)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
       auto load_a_group = [&](int g, int slot) {   // chunks (g_begin+g)*G .. of the weight panel -> A slots slot*G ..
         const int c0 = (g_begin + g) * G, n = min(G, kiters - c0);
-        mbar_expect_tx(&fullA[slot], n * TG_A_BYTES);
+        mbar_expect_tx_pred(&fullA[slot], n * TG_A_BYTES, leader);
         int term = c0 / p.kchunks, kc = c0 % p.kchunks;
         for (int i = 0; i < n; ++i) {
-          tma_load_2d(sA + (slot * G + i) * TG_A_BYTES, &tmW, &fullA[slot], (term == 1 ? p.w_lo_off : 0) + kc * TG_BK, ftile * TG_BM);
+          tma_load_2d_pred(sA + (slot * G + i) * TG_A_BYTES, &tmW, &fullA[slot], (term == 1 ? p.w_lo_off : 0) + kc * TG_BK, ftile * TG_BM, leader);
           if (++kc == p.kchunks) { kc = 0; ++term; }
         }
       };
       const int npre = ngroups < NG ? ngroups : NG;
       for (int g = 0; g < npre; ++g) load_a_group(g, g);   // static weights: issued before the grid dependency resolves
       pdl_wait();
-      DBG(2);
+      if (leader) DBG(2);
       int gA = 0, gB = 0;                          // groups issued so far
       for (int rt = rt0; rt < rt1; ++rt) {
         for (int g = 0; g < ngroups; ++g) {
@@ -158,10 +160,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
           }
           if (gB >= NG) mbar_wait(&emptyB[sb], ((gB / NG) & 1) ^ 1);
           const int c0 = (g_begin + g) * G, n = min(G, kiters - c0);
-          mbar_expect_tx(&fullB[sb], n * B_BYTES);
+          mbar_expect_tx_pred(&fullB[sb], n * B_BYTES, leader);
           int term = c0 / p.kchunks, kc = c0 % p.kchunks;
           for (int i = 0; i < n; ++i) {
-            tma_load_2d(sB + (sb * G + i) * B_BYTES, term == 2 ? &tmX_lo : &tmX_hi, &fullB[sb], kc * TG_BK, rt * BN);
+            tma_load_2d_pred(sB + (sb * G + i) * B_BYTES, term == 2 ? &tmX_lo : &tmX_hi, &fullB[sb], kc * TG_BK, rt * BN, leader);
             if (++kc == p.kchunks) { kc = 0; ++term; }
           }
           ++gB;

@@ -92,36 +92,39 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   constexpr uint32_t IDESC = umma_idesc_bf16(128, XA_NROWS);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // convergent warp, one elected lane issues (see umma_bf16_pred in common.cuh)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
       // per-batch constants: before the grid dependency resolves
-      mbar_expect_tx(fullA1, 8 * XA_CHUNK_A);
-      for (int i = 0; i < 8; ++i) tma_load_2d(sA1 + i * XA_CHUNK_A, &tmM, fullA1, i * 64, opnd * 128);
+      mbar_expect_tx_pred(fullA1, 8 * XA_CHUNK_A, leader);
+      for (int i = 0; i < 8; ++i) tma_load_2d_pred(sA1 + i * XA_CHUNK_A, &tmM, fullA1, i * 64, opnd * 128, leader);
       for (int ft = 0; ft < 2; ++ft) {
-        mbar_expect_tx(&fullA2[ft], 2 * XA_CHUNK_A);
+        mbar_expect_tx_pred(&fullA2[ft], 2 * XA_CHUNK_A, leader);
         for (int c = 0; c < 2; ++c)
-          tma_load_2d(sA2 + (ft * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128);
+          tma_load_2d_pred(sA2 + (ft * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128, leader);
       }
       pdl_wait();
-      XDBG(1);
-      mbar_expect_tx(fullB1, 8 * XA_CHUNK_B);
-      for (int i = 0; i < 8; ++i) tma_load_2d(sB1 + i * XA_CHUNK_B, &tmX, fullB1, i * 64, b * p.beam);
+      if (leader) XDBG(1);
+      mbar_expect_tx_pred(fullB1, 8 * XA_CHUNK_B, leader);
+      for (int i = 0; i < 8; ++i) tma_load_2d_pred(sB1 + i * XA_CHUNK_B, &tmX, fullB1, i * 64, b * p.beam, leader);
       // feature tiles 2,3 of Nt_b go into the upper half of the Mt_b area as soon as chain 1 has consumed it, so their
       // load latency overlaps the softmax instead of sitting between the two MMA chains
       mbar_wait(tfull1, 0);
       for (int ft = 2; ft < 4; ++ft) {
-        mbar_expect_tx(&fullA2[ft], 2 * XA_CHUNK_A);
+        mbar_expect_tx_pred(&fullA2[ft], 2 * XA_CHUNK_A, leader);
         for (int c = 0; c < 2; ++c)
-          tma_load_2d(sA1 + (4 + (ft - 2) * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128);
+          tma_load_2d_pred(sA1 + (4 + (ft - 2) * 2 + c) * XA_CHUNK_A, &tmN, &fullA2[ft], c * 64, opnd * 512 + ft * 128, leader);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    {
       // ---- chain 1: scores^T
       mbar_wait(fullA1, 0);
-      XDBG(2);
+      if (leader) XDBG(2);
       mbar_wait(fullB1, 0);
-      XDBG(3);
+      if (leader) XDBG(3);
       tc_fence_after();
       {
         const uint64_t a0 = umma_desc_sw128(smem_u32(sA1));
@@ -130,30 +133,30 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, a0 + (uint64_t)(i * (XA_CHUNK_A >> 4) + 2 * k), b0 + (uint64_t)(i * (XA_CHUNK_B >> 4) + 2 * k), IDESC,
-                      (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_pred(tmem_base, a0 + (uint64_t)(i * (XA_CHUNK_A >> 4) + 2 * k), b0 + (uint64_t)(i * (XA_CHUNK_B >> 4) + 2 * k), IDESC,
+                      (i > 0 || k > 0) ? 1u : 0u, leader);
       }
-      umma_commit(tfull1);
-      XDBG(4);
+      umma_commit_pred(tfull1, leader);
+      if (leader) XDBG(4);
       // ---- chain 2: outputs^T, four feature tiles of 128
       mbar_wait(pready, 0);
-      XDBG(7);
+      if (leader) XDBG(7);
       tc_fence_after();
       const uint64_t pb0 = umma_desc_sw128(smem_u32(sB2));
       for (int ft = 0; ft < 4; ++ft) {
         mbar_wait(&fullA2[ft], 0);
-        if (ft == 2) XDBG(8);
+        if (ft == 2) if (leader) XDBG(8);
         tc_fence_after();
         const uint64_t a0 = umma_desc_sw128(smem_u32(ft < 2 ? sA2 + ft * 2 * XA_CHUNK_A : sA1 + (4 + (ft - 2) * 2) * XA_CHUNK_A));
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + 32 + ft * XA_NROWS, a0 + (uint64_t)(c * (XA_CHUNK_A >> 4) + 2 * k),
-                      pb0 + (uint64_t)(c * (XA_CHUNK_B >> 4) + 2 * k), IDESC, (c > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_pred(tmem_base + 32 + ft * XA_NROWS, a0 + (uint64_t)(c * (XA_CHUNK_A >> 4) + 2 * k),
+                      pb0 + (uint64_t)(c * (XA_CHUNK_B >> 4) + 2 * k), IDESC, (c > 0 || k > 0) ? 1u : 0u, leader);
       }
-      umma_commit(tfull2);
-      XDBG(9);
+      umma_commit_pred(tfull2, leader);
+      if (leader) XDBG(9);
     }
     __syncwarp();
   } else {
