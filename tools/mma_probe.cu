@@ -7,7 +7,9 @@ namespace fpnmt { void set_last_error(const std::string&) {} bool pdl_enabled() 
 
 __device__ __forceinline__ long long gt() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-// mode bit0: distinct A slot per k-iter; bit1: commit to a side barrier every 4 MMAs; bit2: warps 2,3 spin on the final barrier
+// mode bit0: distinct A slot per k-iter; bit1: commit to a side barrier every 4 MMAs; bit2: warps 2,3 spin on the final barrier;
+// bit3: second issuer; bit4: CONVERGENT issue (the whole warp runs the loop, one elected lane issues through the predicated
+// forms) instead of an `if (lane == 0)` region, where ptxas wraps every UTCHMMA in an ELECT / R2UR retry loop
 template <int BN>
 __global__ void __launch_bounds__(128, 1) probe(int n_mma, int distinct_a, long long* out) {
   extern __shared__ uint8_t raw[];
@@ -26,7 +28,29 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, int distinct_a, long 
   tc_fence_after();
   const uint32_t tm = slot;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
-  if (warp == 1 && lane == 0) {
+  if ((distinct_a & 16) && warp == 1) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    long long g0 = gt();
+    long long t0 = clock64();
+    for (int it = 0; it < n_mma / 4; ++it) {
+      const int ka = (distinct_a & 1) ? it % 4 : 0;
+      const uint64_t ad = umma_desc_sw128(smem_u32(smem + ka * 16384));
+      const uint64_t bd = umma_desc_sw128(smem_u32(smem + 4 * 16384 + (it % 4) * BN * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_pred(tm, ad + 2 * k, bd + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u, leader);
+      if (distinct_a & 2) umma_commit_pred(&side[it % 8], leader);
+    }
+    long long t1 = clock64();
+    umma_commit_pred(&bar, leader);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    long long g1 = gt();
+    if (leader) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+      out[2] = g1 - g0;
+    }
+  } else if (!(distinct_a & 16) && warp == 1 && lane == 0) {
     long long g0 = gt();
     long long t0 = clock64();
     for (int it = 0; it < n_mma / 4; ++it) {
@@ -77,7 +101,10 @@ void run(int n, int da) {
 }
 
 int main() {
-  for (int da = 0; da < 16; da += 8) {
+  const int modes[4] = {1, 17, 3, 19};   // lane-0 vs convergent issue, without / with a commit every 4 MMAs
+  for (int mi = 0; mi < 4; ++mi) {
+    const int da = modes[mi];
+    run<16>(256, da);
     run<32>(32, da); run<32>(256, da);
     run<64>(32, da); run<64>(256, da);
     run<128>(32, da); run<128>(256, da);
