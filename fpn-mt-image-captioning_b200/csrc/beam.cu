@@ -128,12 +128,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
 #pragma unroll 4
     for (int i = 0; i < nv4; ++i) {
       const float4 q = s_row4[i * THREADS + tid];
-      sum += expf(q.x - tmax_v) + expf(q.y - tmax_v) + expf(q.z - tmax_v) + expf(q.w - tmax_v);   // exp(-inf) = 0: padding
+      // __expf (2^x on the SFU, ~2 ulp): the sum only enters lse, where 1e-7 relative is far below the parity tolerance;
+      // the candidate scores themselves (cand(), prob mode) keep the accurate expf
+      sum += __expf(q.x - tmax_v) + __expf(q.y - tmax_v) + __expf(q.z - tmax_v) + __expf(q.w - tmax_v);   // exp(-inf) = 0: padding
     }
   }
   {
     const float wm = warp_max(tmax_v);
-    sum = warp_sum(tmax_v > -INFINITY ? sum * expf(tmax_v - wm) : 0.f);
+    sum = warp_sum(tmax_v > -INFINITY ? sum * __expf(tmax_v - wm) : 0.f);
     if (lane == 0) {
       s_m[warp] = wm;
       s_s[warp] = sum;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   for (int w = 1; w < NW; ++w) m = fmaxf(m, s_m[w]);
   sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < NW; ++w) sum += s_s[w] * expf(s_m[w] - m);
+  for (int w = 0; w < NW; ++w) sum += s_s[w] * __expf(s_m[w] - m);
   // ---- candidate score of a logit (pipeline.py:117,122 in prob mode; the same ordering in the log domain otherwise).
   // Every step of it is monotone non-decreasing in floating point, so max_e cand(v_e) == cand(max_e v_e) exactly.
   const float lse = m + logf(sum);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   // ranked by counting (rank = number of better entries; no serial arg-max rounds).  If more than CAP elements reach tau
   // (massive ties, e.g. the reference's probability underflow regime where every candidate is 0), the exact but slower
   // rescan path below takes over.  Every warp derives tau redundantly from the shared maxima: no extra barrier.
-  float tau;
+  float tau, tau_raw;
   {
     float g = s_cv[lane];
 #pragma unroll
@@ -178,21 +180,32 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       rank += (gj > g || (gj == g && j < lane)) ? 1 : 0;
     }
     const unsigned hit = __ballot_sync(0xffffffffu, rank == N - 1);      // ranks are a permutation of 0..31
-    tau = cand(__shfl_sync(0xffffffffu, g, __ffs(hit) - 1));
+    tau_raw = __shfl_sync(0xffffffffu, g, __ffs(hit) - 1);
+    tau = cand(tau_raw);
   }
+  // Raw-logit pre-filter: cand() is monotone non-decreasing, so if cand(v_lo) < tau STRICTLY, every element below v_lo has
+  // c <= cand(v_lo) < tau and cannot qualify; the exact comparison runs on the survivors.  When the plateau of equal
+  // candidate scores reaches the margin (probability underflow, dead beams: all candidates tie) the filter is disabled
+  // and the tie handling below sees every element, exactly as before.
+  const float v_lo0 = tau_raw - 1e-2f * fmaxf(1.f, fabsf(tau_raw));
+  const float v_lo = (cand(v_lo0) < tau) ? v_lo0 : -INFINITY;
   {
 #pragma unroll 2
     for (int i = 0; i < nv4; ++i) {
       const float4 q = s_row4[i * THREADS + tid];
-      const float c4[4] = {cand(q.x), cand(q.y), cand(q.z), cand(q.w)};
+      const float v4[4] = {q.x, q.y, q.z, q.w};
+      if (!(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)) >= v_lo)) continue;      // the common case: nothing near the threshold
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int e = (i * THREADS + tid) * 4 + j;
-        if (e < V && c4[j] >= tau) {
-          const int pos = atomicAdd(&s_cnt, 1);
-          if (pos < CAP) {
-            s_lv[pos] = c4[j];
-            s_li[pos] = e;
+        if (e < V && v4[j] >= v_lo) {
+          const float c = cand(v4[j]);
+          if (c >= tau) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < CAP) {
+              s_lv[pos] = c;
+              s_li[pos] = e;
+            }
           }
         }
       }
@@ -209,8 +222,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       for (int j = 0; j < cnt; ++j) rank += better(s_lv[j], s_li[j], v, e) ? 1 : 0;
       if (rank < N) {
         st.cand_val[(size_t)row * N + rank] = v;
-        st.cand_idx[(size_t)row * N + rank] = e;
-        __threadfence();                                    // visible before the image counter moves
+        st.cand_idx[(size_t)row * N + rank] = e;            // published by the block barrier + thread 0's fence below
       }
     }
   } else {
