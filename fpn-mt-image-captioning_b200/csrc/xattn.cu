@@ -23,7 +23,8 @@ constexpr int XA_SCR_STRIDE = 516;                       // floats per row of th
                                                          // rows, 4-bank skew: float4 reads of 8 consecutive rows are conflict-free)
 constexpr int XA_TMEM_COLS = 128;
 
-size_t xattn_smem_bytes() { return XA_OFF_BARS + 256 + 1024; }
+constexpr int XA_OFF_VEC = XA_OFF_BARS + 256;               // float [3][512]: output bias, LayerNorm gamma, beta (static)
+size_t xattn_smem_bytes() { return XA_OFF_VEC + 3 * 512 * 4 + 1024; }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -45,6 +46,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   uint8_t* sB2 = smem + XA_OFF_B2;
   float2* sPart = reinterpret_cast<float2*>(smem + XA_OFF_PART);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XA_OFF_BARS);
+  float* sVec = reinterpret_cast<float*>(smem + XA_OFF_VEC);
   uint64_t* fullA1 = bars;          // Mt_b landed
   uint64_t* fullB1 = bars + 1;      // out1 rows landed
   uint64_t* fullA2 = bars + 2;      // [4] feature tile ft of Nt_b landed
@@ -165,6 +167,15 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     const int L = quarter * 32 + lane;            // (head, token) pair == TMEM lane == K index of chain 2
     const int t = e * 32 + lane;                  // 0..127
     const int lrow = t & 15, part = t >> 4;       // LayerNorm phase: row of the image, 64-feature slice
+    // static per-layer vectors -> shared memory while the kernel is still waiting for its inputs (128 threads x 3 x 16 B)
+    {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const float* g = v == 0 ? p.obias : v == 1 ? p.gamma : p.beta;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sVec + v * 512 + t * 4)), "l"(g + t * 4) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const float sb = __ldg(p.sbias + (size_t)opnd * XA_PAIRS + L);
     pdl_wait();
     const int grow = b * p.beam + lrow;           // global row handled in the LayerNorm phase
@@ -224,6 +235,8 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     mbar_wait(tfull2, 0);
     tc_fence_after();
     if (t == 0) XDBG(10);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // every thread's slice of the staged vectors is visible
     {
       uint32_t r[2][32];                          // the four 16-column accumulators are contiguous: two 32-column loads
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 32, r[0]);
@@ -232,7 +245,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
 #pragma unroll
       for (int ft = 0; ft < 4; ++ft) {
         const int f = ft * 128 + L;
-        const float ob = __ldg(p.obias + f);
+        const float ob = sVec[f];
 #pragma unroll
         for (int c = 0; c < 16; ++c) scr[c * XA_SCR_STRIDE + f] = __uint_as_float(r[ft >> 1][(ft & 1) * 16 + c]) + ob;
       }
@@ -281,10 +294,10 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const int f0 = part * 64 + g * 8;
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + f0));
-        const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gamma + f0 + 4));
-        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + f0));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + f0 + 4));
+        const float4 ga = *reinterpret_cast<const float4*>(sVec + 512 + f0);
+        const float4 gb = *reinterpret_cast<const float4*>(sVec + 512 + f0 + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(sVec + 1024 + f0);
+        const float4 bb = *reinterpret_cast<const float4*>(sVec + 1024 + f0 + 4);
         const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
         const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
         float o[8];
