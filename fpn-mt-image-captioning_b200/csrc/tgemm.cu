@@ -18,7 +18,7 @@ constexpr int TG_LN_BYTES = 32 * TG_LN_STRIDE * 4 + 128;
 
 size_t tgemm_smem_bytes(int BN) {
   return (size_t)TG_A_SLOTS * TG_A_BYTES + (size_t)TG_B_STAGES * BN * TG_BK * 2 + TG_LN_BYTES + 4 * 32 * 8 /*partials*/ +
-         32 * 8 /*cta stats*/ + 512 /*barriers*/ + 1024 /*align slack*/;
+         32 * 8 /*cta stats*/ + 2 * TG_BM * 4 /*LayerNorm gamma, beta of the tile*/ + 512 /*barriers*/ + 1024 /*align slack*/;
 }
 
 __device__ __forceinline__ long long tg_timer() {
@@ -54,7 +54,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
   float* sLN = reinterpret_cast<float*>(sB + TG_B_STAGES * B_BYTES);
   float2* sPart = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sLN) + TG_LN_BYTES);   // [4][32] (mean, M2)
   float2* sStat = sPart + 4 * 32;                                                            // [32] CTA-level (mean, M2)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 32);
+  float* sGB = reinterpret_cast<float*>(sStat + 32);                                         // [2][128] gamma, beta of this feature tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sGB + 2 * TG_BM);
   uint64_t* fullA = bars;                          // [8]
   uint64_t* emptyA = bars + TG_A_SLOTS;            // [8]
   uint64_t* fullB = bars + 2 * TG_A_SLOTS;         // [8]
@@ -240,6 +241,11 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool direct_f32 = !is_ln && p.out_f32 != nullptr && p.out.p == nullptr && !p.has_res && p.act != ACT_RELU6;
+    if (is_ln && e < 2) {   // static LayerNorm parameters of this feature tile -> shared memory, before the dependency resolves
+      const float* g = (e == 0 ? p.gamma : p.beta) + ftile * TG_BM + lane * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sGB + e * TG_BM + lane * 4)), "l"(g) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     pdl_wait();
     if (helper_b && e == 0 && lane == 0) {
       const int n = kiters - G;
@@ -395,6 +401,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
             m2 = fmaf(d, d, m2);
           }
           sPart[e * 32 + lane] = make_float2(m, m2);
+          asm volatile("cp.async.wait_group 0;" ::: "memory");   // the staged gamma / beta (issued before the grid dependency)
           asm volatile("bar.sync 1, 128;" ::: "memory");
           {
             const float2 a0 = sPart[lane], a1 = sPart[32 + lane], a2 = sPart[64 + lane], a3 = sPart[96 + lane];
@@ -414,10 +421,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float o[8];
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + fo + g * 8));
-              const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gamma + fo + g * 8 + 4));
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + fo + g * 8));
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + fo + g * 8 + 4));
+              const float4 ga = *reinterpret_cast<const float4*>(sGB + e * 32 + g * 8);
+              const float4 gb = *reinterpret_cast<const float4*>(sGB + e * 32 + g * 8 + 4);
+              const float4 ba = *reinterpret_cast<const float4*>(sGB + TG_BM + e * 32 + g * 8);
+              const float4 bb = *reinterpret_cast<const float4*>(sGB + TG_BM + e * 32 + g * 8 + 4);
               const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
               const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
