@@ -37,7 +37,12 @@ def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(bdir, exist_ok=True)
     stamp_file = os.path.join(bdir, "stamp")
     stamp = _stamp()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+
+    def lib_id() -> str:    # the stamp also pins the library file itself (a copied-over .so must not pass as up to date)
+        st = os.stat(OUT)
+        return "%d:%d" % (st.st_size, st.st_mtime_ns)
+
+    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp + " " + lib_id():
         return OUT
 
     def cc(src):
@@ -54,7 +59,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    open(stamp_file, "w").write(stamp)
+    open(stamp_file, "w").write(stamp + " " + lib_id())
     if verbose:
         print("built", OUT)
     return OUT
