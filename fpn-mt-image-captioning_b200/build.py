@@ -39,8 +39,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     stamp = _stamp()
 
     def lib_id() -> str:    # the stamp also pins the library file itself (a copied-over .so must not pass as up to date)
-        st = os.stat(OUT)
-        return "%d:%d" % (st.st_size, st.st_mtime_ns)
+        return hashlib.sha256(open(OUT, "rb").read()).hexdigest()[:16]    # content, not mtime: the file is copied to the GPU box
 
     if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp + " " + lib_id():
         return OUT
