@@ -364,6 +364,29 @@ def run_own(args, wl):
     roofline["encode_us_sum"] = sum(o["us"] for o in enc_ops)
     roofline["decode_step_us_sum"] = sum(o["us"] for o in step_ops)
     roofline["decode_step_kernels"] = len(step_ops)
+    # ---- fp32-class parity mode (BF16X3: 3-term split-bf16 products, the mode that meets the 2e-3 log-prob / 99 % sequence
+    # bound): same workload, same call, device-resident inputs, timed the same way; N = 1 only
+    parity_mode = None
+    if world == 1 and args.precision == "bf16" and not args.no_parity_mode:
+        eng.close()
+        w3 = init_weights(wl["backbone"], vocab=V, seed=0)
+        eng3 = Engine(w3, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision="bf16x3", score_mode="log",
+                      use_graphs=not args.no_graphs, device=local)
+        del w3
+        for i in range(3):
+            eng3.generate(dev_imgs[i % 2], early_stop=False, to_host=False)
+        torch.cuda.synchronize()
+        k3 = max(2, min(args.steps, 4))
+        e0.record(stream)
+        for i in range(k3):
+            eng3.generate(dev_imgs[i % 2], early_stop=False, to_host=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1) / k3
+        parity_mode = {"precision": "bf16x3", "value": B / (ms3 * 1e-3), "unit": "images/s", "ms_per_step": ms3, "steps": k3,
+                       "note": "same workload in the fp32-class mode whose parity bound is the north star's (log-probs 2e-3, "
+                               ">= 99 % identical sequences: tests/test_gpu_captions.py); the headline `value` is the bf16 mode"}
+        eng3.close()
     cb = None
     if world == 1 and not args.no_cpu:
         cb = cpu_reference_sample(wl, 3, 1)
@@ -382,6 +405,7 @@ def run_own(args, wl):
                     "api": "Engine.generate_stream (fpnmt_stage_images + fpnmt_generate_staged; double-buffered input)",
                     "unpipelined_value": total_images / (ms_e2e_sync * 1e-3)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
+            "parity_mode": parity_mode,
             "model_tflops": flop_total / (ms * 1e-3) / 1e12,
             "ids_checksum": int(ids_check.to(torch.int64).sum().item())}
     print(json.dumps(line), flush=True)
@@ -397,6 +421,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 throughput leg (parity_mode key)")
     ap.add_argument("--profile-iters", type=int, default=10)
     ap.add_argument("--profile-out", default=None, help="write the engine's per-op profile (JSON) here")
     ap.add_argument("--ncu-step", action="store_true", help="bracket one warm step with cudaProfilerStart/Stop (for ncu launch lists)")

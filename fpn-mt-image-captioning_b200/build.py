@@ -32,7 +32,9 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, dbg_stamps: bool = False) -> str:
+    if dbg_stamps:    # developer build: globaltimer timelines inside the tcgen05 kernels (FPNMT_DBG_OP=<op name>)
+        FLAGS.append("-DFPNMT_DBG_STAMPS")
     bdir = os.path.join(CSRC, "build")
     os.makedirs(bdir, exist_ok=True)
     stamp_file = os.path.join(bdir, "stamp")
@@ -65,4 +67,4 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    build(force="--force" in sys.argv, dbg_stamps="--dbg-stamps" in sys.argv)

@@ -11,20 +11,10 @@
 namespace fpnmt {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("FPNMT_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
-bool pdl_small_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("FPNMT_PDL");
-    return !(e && (e[0] == '0' || e[0] == '2'));
-  }();
-  return on;
-}
+static int g_pdl_mode = 1;   // 0 = off, 1 = every kernel, 2 = tcgen05 GEMM kernels only (fpnmt_config.kernel_opts)
+void set_pdl_mode(int mode) { g_pdl_mode = mode; }
+bool pdl_enabled() { return g_pdl_mode != 0; }
+bool pdl_small_enabled() { return g_pdl_mode == 1; }
 }  // namespace fpnmt
 
 using namespace fpnmt;

@@ -317,20 +317,20 @@ __global__ void __launch_bounds__(EA_WARPS * 32) k_enc_attention_mma(Act q, EncA
   }
 }
 
+// Function attributes are per device: called from Engine::init for every device an engine is created on.
+int attention_set_attributes() {
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+  return 0;
+}
+
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
-                         int out_col, cudaStream_t s) {
+                         int out_col, bool force_simt, cudaStream_t s) {
   if (Tq > 16) {
     set_last_error("enc_attention: Tq must be <= 16");
     return 1;
   }
   dim3 grid(B, heads);
-  const char* force_simt = getenv("FPNMT_ENC_ATT_SIMT");   // test hook: compare the two paths on identical inputs
-  if (!kv.lo && !q.lo && !out.lo && !(force_simt && force_simt[0] == '1')) {   // bf16 mode: tensor-core flash kernel
-    static bool attr_done = false;
-    if (!attr_done) {
-      FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
-      attr_done = true;
-    }
+  if (!kv.lo && !q.lo && !out.lo && !force_simt) {   // bf16 mode: tensor-core flash kernel
     if (q_col != out_col) {
       set_last_error("enc_attention: the tensor-core path writes the output at the query's column block");
       return 1;
@@ -364,11 +364,6 @@ int launch_enc_attention_views(Act q, const Act* kvs, const int* tks, const int*
     views.kv[v] = kvs[v];
     views.Tk[v] = tks[v];
     views.col[v] = cols[v];
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
-    attr_done = true;
   }
   FPNMT_CUDA_OK(launch_k(k_enc_attention_mma, dim3(B, heads, nviews), dim3(EA_WARPS * 32), (size_t)EA_SMEM, s, q, views, k_col, v_col,
                          Tq, out));

@@ -79,8 +79,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   __shared__ int s_last;
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  long long* dbg = (st.dbg && row < st.N) ? st.dbg + 16 : nullptr;       // timeline of image 0 (its last block: phase 2)
+#ifdef FPNMT_DBG_STAMPS   // build.py --dbg-stamps (see igemm.cu): timeline of image 0 (its last block: phase 2)
+  long long* dbg = (st.dbg && row < st.N) ? st.dbg + 16 : nullptr;
 #define BDBG(k) do { if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[k] = t_; } } while (0)
+#else
+#define BDBG(k) do { } while (0)
+#endif
   if (row == 0) BDBG(0);
   pdl_launch();
   pdl_wait();
@@ -412,6 +416,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   }
   BDBG(12);
 }
+int beam_set_attributes() {   // per device (Engine::init)
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return 0;
+}
 int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s) {
   if (st.N > 32 || (ld & 3)) {
     set_last_error("beam_step: beam width must be <= 32 and logits ld a multiple of 4");
@@ -424,12 +433,6 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
   if (nv4 > 32 || smem > 200 * 1024) {
     set_last_error("beam_step: vocabulary too large (max 65536)");
     return 1;
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_beam_step<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
   }
   if (threads == 256)
     FPNMT_CUDA_OK(launch_k_small(k_beam_step<256>, dim3(st.B * st.N), dim3(256), smem, s, st, logits, ld, em));

@@ -498,14 +498,14 @@ int launch_conv3x3_c1(Act in, const float* w, const float* bias, int N, int H, i
     set_last_error("conv3x3_c1: needs a plain bf16 256-channel input");
     return 1;
   }
-  static bool attr_done = false;
   const size_t smem = (size_t)SC_HALO * SC_HALO * SC_PITCH;
-  if (!attr_done) {
-    FPNMT_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_c1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   const dim3 grid((W + SC_TILE - 1) / SC_TILE, (H + SC_TILE - 1) / SC_TILE, N);
   FPNMT_CUDA_OK(launch_k(k_conv3x3_c1, grid, dim3(256), smem, s, in, w, bias, N, H, W, out));
+  return 0;
+}
+
+int elementwise_set_attributes() {   // per device (Engine::init)
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_c1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SC_HALO * SC_HALO * SC_PITCH)));
   return 0;
 }
 

@@ -76,13 +76,34 @@ int Engine::init() {
   RC(igemm_set_attributes());
   RC(tgemm_set_attributes());
   RC(xattn_set_attributes());
-  if (const char* e = getenv("FPNMT_XATTN")) use_xattn_ = !(e[0] == '0');
-  if (const char* e = getenv("FPNMT_STEM")) use_stem_ = !(e[0] == '0');
+  RC(elementwise_set_attributes());
+  RC(attention_set_attributes());
+  RC(beam_set_attributes());
   RC(stem_set_attributes());
-  if (const char* e = getenv("FPNMT_TGEMM")) use_tgemm_ = !(e[0] == '0');
+  use_xattn_ = !(c.kernel_opts & FPNMT_OPT_NO_XATTN);
+  use_stem_ = !(c.kernel_opts & FPNMT_OPT_NO_STEM);
+  use_tgemm_ = !(c.kernel_opts & FPNMT_OPT_NO_TGEMM);
+  set_pdl_mode((c.kernel_opts & FPNMT_OPT_NO_PDL) ? 0 : (c.kernel_opts & FPNMT_OPT_PDL_GEMM_ONLY) ? 2 : 1);
+  if (c.cache_mode < 0 || c.cache_mode > 1 || c.decode_path < 0 || c.decode_path > 1 || c.dec_groups < 0 || c.length_penalty < 0.f)
+    return fail(FPNMT_ERR_INVALID, "bad cache_mode / decode_path / dec_groups / length_penalty");
   FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
   FPNMT_CUDA_OK(cudaMallocHost(&h_pinned_, 64));
   return 0;
+}
+
+// Timeline buffer for the op named by FPNMT_DBG_OP - only in builds with -DFPNMT_DBG_STAMPS (build.py --dbg-stamps); the
+// product build has neither the stamps in the kernels nor this environment lookup.
+long long* Engine::dbg_timeline(const std::string& name) {
+#ifdef FPNMT_DBG_STAMPS
+  const char* dn = getenv("FPNMT_DBG_OP");
+  if (dn && name == dn) {
+    dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
+    if (dbg_buf_) cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+    return dbg_buf_;
+  }
+#endif
+  (void)name;
+  return nullptr;
 }
 
 void* Engine::dalloc(size_t bytes) {
@@ -302,13 +323,7 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   if (res) r = res->a;
   // a K-padded weight (stem im2col) is addressed with Cin == K
   RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_));
-  if (const char* dn = getenv("FPNMT_DBG_OP")) {
-    if (name == dn) {
-      dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-      cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
-      op.p.dbg = dbg_buf_;
-    }
-  }
+  op.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;
   o.kind = "igemm";
@@ -327,14 +342,8 @@ int Engine::add_dense(Program& prog, const std::string& name, const Tensor& in, 
   const int R = (int)in.pixels();
   TgemmOp op;
   RC(make_tgemm_op(&op, R, in.a, gw.w, gw.Cout, gw.K, split_, gw.bias, act, out.a, out_f32, ld_f32, res ? &res->a : nullptr,
-                   gamma, beta, 1e-6f, num_sms_));
-  if (const char* dn = getenv("FPNMT_DBG_OP")) {
-    if (name == dn) {
-      dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-      cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
-      op.p.dbg = dbg_buf_;
-    }
-  }
+                   gamma, beta, 1e-6f, num_sms_, 0, (cfg_.kernel_opts & FPNMT_OPT_KSPLIT2) != 0));
+  op.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;
   o.kind = "tgemm";
@@ -355,13 +364,7 @@ int Engine::add_stem(Program& p, const std::string& name, int kh, int pad, int c
   bf16* wp = (bf16*)dalloc((size_t)cout * ks * ks * 12 * sizeof(bf16));
   if (!wp) return FPNMT_ERR_CUDA;
   RC(make_stem_op(&so, img_slot_, B, S, S, kh, pad, cout, gw.w, Kp, wp, gw.bias, act, out.a, num_sms_));
-  if (const char* dn = getenv("FPNMT_DBG_OP")) {
-    if (name == dn) {
-      dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-      cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
-      so.p.dbg = dbg_buf_;
-    }
-  }
+  so.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;
   o.kind = "igemm";
@@ -772,8 +775,8 @@ int Engine::build_mt_encoder(Program& p) {
     RC(prep_dense_cat({e + "/ffn2"}, &g2));
     Tensor q = rows_act(R, 4 * D), att = rows_act(R, 4 * D);
     RC(add_conv(p, ln + "_q", base, gq, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, q));
-    const char* force_simt = getenv("FPNMT_ENC_ATT_SIMT");
-    if (!split_ && !(force_simt && force_simt[0] == '1')) {
+    const bool force_simt = (cfg_.kernel_opts & FPNMT_OPT_ENC_ATT_SIMT) != 0;
+    if (!split_ && !force_simt) {
       // bf16 mode: the four cross-level attentions of the layer as one launch (long view first)
       struct V4 { Act kv[4]; int tk[4]; int col[4]; } v4;
       double bytes = 0, flops = 0;
@@ -795,7 +798,7 @@ int Engine::build_mt_encoder(Program& p) {
       Act qa = q.a, ka = kv[v].a, oa = att.a;
       const int tk = ntok[v], tq = n_base_, kc = l * 2 * D, vc = l * 2 * D + D, qc = v * D;
       Op o = ew_op(ln + "_attn_view" + std::to_string(v),
-                   [=](cudaStream_t s) { return launch_enc_attention(qa, qc, ka, kc, vc, B, tq, tk, H, oa, qc, s); },
+                   [=](cudaStream_t s) { return launch_enc_attention(qa, qc, ka, kc, vc, B, tq, tk, H, oa, qc, force_simt, s); },
                    (double)B * tk * 2 * D * 2, "attention");
       o.flops = 4.0 * B * tq * tk * D;
       p.push_back(std::move(o));
@@ -1024,13 +1027,7 @@ int Engine::build_decoder() {
         if (xattn) {
           XattnOp xo;
           RC(make_xattn_op(&xo, xMt, xNt, L, B, b0, Bg, N, l, xSb, w.go2.bias, w.lnp[2], w.lnp[3], out1.a, out2.a));
-          if (const char* dn = getenv("FPNMT_DBG_OP")) {
-            if (ln + "_xattn" == dn) {
-              dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-              cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
-              xo.p.dbg = dbg_buf_;
-            }
-          }
+          xo.p.dbg = dbg_timeline(ln + "_xattn");
           Op o;
           o.name = ln + "_xattn(q2+cross_attn+o2+res+ln)" + sfx;
           o.kind = "xattn";
@@ -1069,21 +1066,14 @@ int Engine::build_decoder() {
       }
       return 0;
     };
-    if (const char* dn = getenv("FPNMT_DBG_OP")) {
-      if (std::string(dn) == "beam_step") {
-        dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-        cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
-        bs_.dbg = dbg_buf_;
-      }
-    }
+    bs_.dbg = dbg_timeline("beam_step");
     RC(build_chain(0, B, bs_, embed_prog_, step_prog_, &beam_embed_));
 
     // ---- decoder groups (opt-in, FPNMT_DEC_GROUPS=G): G independent chains over image slices, run as parallel branches
     // of the decode graph.  Measured on C2 (B200): a half-batch chain alone takes 331 us per step against 385 us for the
     // whole batch, but two of them co-running take 374 us (four quarter chains: 373 us) - about 1 % faster than one
     // chain, so the default stays one chain.
-    int G = 1;
-    if (const char* e = getenv("FPNMT_DEC_GROUPS")) G = atoi(e);
+    int G = cfg_.dec_groups;
     G = std::max(1, std::min(std::min(G, 8), B));
     if (G > 1) {
       groups_.resize(G);

@@ -117,6 +117,7 @@ class Engine {
 
   // helpers
   void* dalloc(size_t bytes);
+  long long* dbg_timeline(const std::string& name);
   Tensor new_act(int N, int H, int W, int C);
   Tensor rows_act(int rows, int C) { return new_act(1, 1, rows, C); }
   static Tensor chan_view(const Tensor& t, int c0, int C);

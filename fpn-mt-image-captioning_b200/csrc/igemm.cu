@@ -78,6 +78,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+#ifdef FPNMT_DBG_STAMPS   // build.py --dbg-stamps: globaltimer timeline of block 0 (FPNMT_DBG_OP=<op name>); off in product builds
   __shared__ long long* s_dbg;
   if (threadIdx.x == 0) {
     s_dbg = nullptr;
@@ -88,6 +89,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   }
 #define DBG(k) do { if (s_dbg) s_dbg[k] = gtimer(); } while (0)
+#else
+#define DBG(k) do { } while (0)
+#endif
 
   pdl_launch();
   if (warp == 0 && lane == 0) {

@@ -4,6 +4,12 @@
 
 namespace fpnmt {
 
+// Opt-in shared-memory sizes are a per-DEVICE function attribute: Engine::init calls these for its device (a static
+// "done once per process" guard would leave a second engine on another GPU of the same process without them).
+int elementwise_set_attributes();
+int attention_set_attributes();
+int beam_set_attributes();
+
 // ---- elementwise.cu -----------------------------------------------------------------------------
 // fp32 NHWC image (pointer read from a device slot so a captured graph can be re-pointed) -> im2col matrix [N*Ho*Wo][Kpad] for the Cin=3 stem convolutions (k = (ky*kw+kx)*3+c).
 int launch_im2col_stem(const float* const* img_slot, int N, int H, int W, int kh, int kw, int stride, int pad_t, int pad_l, int Ho,
@@ -40,8 +46,9 @@ int launch_act_to_f32(Act in, size_t rows, float* out, cudaStream_t s);
 
 // ---- attention.cu -------------------------------------------------------------------------------
 // Encoder cross-level attention for one (layer, view): q (B*16 rows) vs K/V of a static view (B*Tk rows).
+// force_simt: fp32 CUDA-core kernel even in bf16 mode (FPNMT_OPT_ENC_ATT_SIMT; compares the two paths on identical inputs)
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
-                         int out_col, cudaStream_t s);
+                         int out_col, bool force_simt, cudaStream_t s);
 // All (<= 4) cross-level attentions of one encoder layer as ONE launch (bf16 mode): view v uses K/V tensor kvs[v] with tks[v]
 // keys and the query / output column block cols[v].
 int launch_enc_attention_views(Act q, const Act* kvs, const int* tks, const int* cols, int nviews, int k_col, int v_col, int B,

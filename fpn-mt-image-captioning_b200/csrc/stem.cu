@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 16 : nullptr;      // FPNMT_DBG_OP timeline of tile 10 (CTA 0)
+#ifdef FPNMT_DBG_STAMPS   // build.py --dbg-stamps (see igemm.cu): timeline of tile 10 (CTA 0)
+  long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 16 : nullptr;
 #define SDBG(k) do { if (dbg && it == 10) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[k] = t_; } } while (0)
+#else
+#define SDBG(k) do { } while (0)
+#endif
   pdl_launch();
   if (warp == 4) {
     if (lane == 0) {
@@ -166,7 +170,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_kernel(const __grid_consta
     if (ntl > 0) stage(0);
     for (int it = 0; it < ntl; ++it) {
       const int b = it & 1, ph = (it >> 1) & 1;
-      if (ptid == 0) { SDBG(0); if (dbg && it == 11) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[12] = t_; } }
+      if (ptid == 0) {
+        SDBG(0);
+#ifdef FPNMT_DBG_STAMPS
+        if (dbg && it == 11) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[12] = t_; }
+#endif
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 2, 256;" ::: "memory");           // patch `it` complete; everyone is done with tile it-1
       if (ptid == 0) SDBG(1);

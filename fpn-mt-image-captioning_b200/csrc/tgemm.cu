@@ -77,6 +77,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
   const int rt1 = min(p.rtiles, rt0 + p.rt_per_item);
   const int kiters = p.nterms * p.kchunks;
 
+#ifdef FPNMT_DBG_STAMPS   // build.py --dbg-stamps: globaltimer timeline of block 0 (FPNMT_DBG_OP=<op name>); off in product builds
   __shared__ long long* s_dbg;
   if (threadIdx.x == 0) {
     s_dbg = nullptr;
@@ -87,6 +88,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CU
     }
   }
 #define DBG(k) do { if (s_dbg) s_dbg[k] = tg_timer(); } while (0)
+#else
+#define DBG(k) do { } while (0)
+#endif
   pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -502,7 +506,7 @@ int tgemm_set_attributes() {
 
 int make_tgemm_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, bool split, const float* bias, int act,
                   const Act& out, float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta,
-                  float eps, int num_sms, int force_bn) {
+                  float eps, int num_sms, int force_bn, bool ksplit2) {
   TgemmParams& p = op->p;
   p = TgemmParams{};
   if (x.C != K) {
@@ -537,10 +541,9 @@ int make_tgemm_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K
   p.ksplit = 1;
   {
     const int groups_all = (p.nterms * p.kchunks + 3) / 4;
-    // Split-K over an 8-CTA cluster is implemented and parity-tested (FPNMT_KSPLIT=2) but OFF by default: on B200 the
+    // Split-K over an 8-CTA cluster is implemented and parity-tested (FPNMT_OPT_KSPLIT2) but OFF by default: on B200 the
     // 8-CTA clusters of 211 KB CTAs schedule so much later that FFN2 went from 12 us to 25 us.
-    const char* e = getenv("FPNMT_KSPLIT");
-    if (e && e[0] == '2' && ln && !p.stationary && groups_all >= 4 && groups_all % 2 == 0) p.ksplit = 2;
+    if (ksplit2 && ln && !p.stationary && groups_all >= 4 && groups_all % 2 == 0) p.ksplit = 2;
   }
   p.bias = bias;
   p.act = act;

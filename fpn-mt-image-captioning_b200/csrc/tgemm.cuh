@@ -60,6 +60,6 @@ int tgemm_set_attributes();
 // x: activation view [R][ld] (C == K); wt: [F][K] bf16 (split: [F][2K]).  BN = 0 selects automatically.
 int make_tgemm_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, bool split, const float* bias, int act,
                   const Act& out, float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta,
-                  float eps, int num_sms, int force_bn = 0);
+                  float eps, int num_sms, int force_bn = 0, bool ksplit2 = false);
 
 }  // namespace fpnmt

@@ -60,6 +60,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   const int b = blockIdx.x;
   const int opnd = p.layer * p.Btot + p.b0 + b;                 // which per-image operand set
 
+#ifdef FPNMT_DBG_STAMPS   // build.py --dbg-stamps (see igemm.cu)
   __shared__ long long* s_dbg;
   if (threadIdx.x == 0) {
     s_dbg = nullptr;
@@ -72,6 +73,9 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     }
   }
 #define XDBG(k) do { if (s_dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); s_dbg[k] = t_; } } while (0)
+#else
+#define XDBG(k) do { } while (0)
+#endif
   pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmM);

@@ -15,12 +15,18 @@ OK, ERR_INVALID, ERR_STATE, ERR_CUDA, ERR_MISSING = 0, 1, 2, 3, 4
 BACKBONE_IDS = {"mobilenet224_1.0": 0, "mobilenetv2": 0, "resnet50": 1, "densenet121": 2}
 PREC_IDS = {"bf16": 0, "bf16x3": 1}
 SCORE_IDS = {"log": 0, "prob": 1}
+CACHE_IDS = {"ancestry": 0, "physical": 1}
+DECODE_IDS = {"auto": 0, "chain": 1}
+# fpnmt_config.kernel_opts bits (include/fpnmt.h FPNMT_OPT_*): each switches one fused kernel back to its unfused equivalent
+OPT_BITS = {"no_xattn": 1, "no_stem": 2, "no_tgemm": 4, "enc_att_simt": 8, "ksplit2": 16, "no_pdl": 32, "pdl_gemm_only": 64}
 
 
 class FpnmtConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "backbone", "image_size", "batch", "beam", "vocab", "max_len", "num_layers", "d_model", "num_heads", "dff",
-        "precision", "score_mode", "start_id", "end_id", "true_beam", "use_graphs")] + [("reserved", C.c_int32 * 8)]
+        "precision", "score_mode", "start_id", "end_id", "true_beam", "use_graphs", "kernel_opts", "cache_mode",
+        "decode_path")] + [("length_penalty", C.c_float), ("finished_beams", C.c_int32), ("dec_groups", C.c_int32),
+                           ("reserved", C.c_int32 * 2)]
 
 
 class FpnmtError(RuntimeError):

@@ -41,7 +41,12 @@ class Engine:
                  num_layers: int = cfg.num_layers, d_model: int = cfg.d_model, num_heads: int = cfg.num_heads,
                  dff: int = cfg.dff, image_size: int = cfg.IMAGE_INPUT_SIZE, precision: str = "bf16",
                  score_mode: str = "log", start_id: int = cfg.START_ID, end_id: int = cfg.END_ID,
-                 true_beam: bool = False, use_graphs: bool = True, device: int = 0):
+                 true_beam: bool = False, use_graphs: bool = True, device: int = 0, opts: Sequence[str] = (),
+                 cache_mode: str = "ancestry", decode_path: str = "auto", length_penalty: float = 0.0,
+                 finished_beams: bool = False, dec_groups: int = 0):
+        """opts: names from _lib.OPT_BITS (e.g. "no_xattn") - each turns one fused kernel back into its unfused equivalent;
+        cache_mode "ancestry" | "physical"; decode_path "auto" (fused cluster-stationary decoder when the configuration
+        allows) | "chain" (per-operator kernels); length_penalty / finished_beams: flagged extensions, 0 = reference."""
         if not torch.cuda.is_available():
             raise RuntimeError("fpnmt.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -59,6 +64,11 @@ class Engine:
         c.score_mode = _lib.SCORE_IDS[score_mode]
         c.start_id, c.end_id = start_id, end_id
         c.true_beam, c.use_graphs = int(true_beam), int(use_graphs)
+        c.kernel_opts = 0
+        for o in opts:
+            c.kernel_opts |= _lib.OPT_BITS[o]
+        c.cache_mode, c.decode_path = _lib.CACHE_IDS[cache_mode], _lib.DECODE_IDS[decode_path]
+        c.length_penalty, c.finished_beams, c.dec_groups = float(length_penalty), int(finished_beams), int(dec_groups)
         self._h = C.c_void_p()
         torch.cuda.init()
         with torch.cuda.device(self.device):

@@ -42,6 +42,19 @@ enum { FPNMT_PREC_BF16 = 0,      /* bf16 operands, fp32 accumulate, bf16 activat
                                     the parity mode; same kernels, 3x the tensor work                        */
 enum { FPNMT_SCORE_LOG = 0,      /* beam score = sum of log-probs                                             */
        FPNMT_SCORE_PROB = 1 };   /* beam score = product of softmax probabilities (reference, pipeline.py:117-123) */
+/* fpnmt_config.kernel_opts: each bit switches ONE fused kernel back to its unfused equivalent (A/B timing and the
+ * fused-vs-unfused parity tests).  0 = every fused path on (the product configuration). */
+enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN kernels instead of xattn_kernel          */
+       FPNMT_OPT_NO_STEM = 2,        /* explicit im2col + GEMM stem instead of stem_kernel                              */
+       FPNMT_OPT_NO_TGEMM = 4,       /* decoder Dense layers through igemm + separate LayerNorm                         */
+       FPNMT_OPT_ENC_ATT_SIMT = 8,   /* CUDA-core encoder attention instead of the tensor-core flash kernel             */
+       FPNMT_OPT_KSPLIT2 = 16,       /* split-K over an 8-CTA cluster for the K = 2048 LayerNorm Dense (slower on B200)  */
+       FPNMT_OPT_NO_PDL = 32,        /* no programmatic dependent launch (process-wide: the last created engine wins)    */
+       FPNMT_OPT_PDL_GEMM_ONLY = 64  /* only the tcgen05 GEMM kernels launch early                                      */ };
+enum { FPNMT_CACHE_ANCESTRY = 0,     /* KV cache never moves; an ancestry table maps (beam, position) -> physical row    */
+       FPNMT_CACHE_PHYSICAL = 1 };   /* KV cache rows are gathered by beam parent after every step (bandwidth kernel)    */
+enum { FPNMT_DECODE_AUTO = 0,        /* cluster-stationary fused decoder (dstep_kernel) whenever the configuration allows */
+       FPNMT_DECODE_CHAIN = 1 };     /* per-operator kernel chain (tgemm / attention / xattn / beam kernels)              */
 
 typedef struct fpnmt_config {
   int32_t backbone;      /* FPNMT_BACKBONE_* — models/mobilenet.py:43, models/resnet.py:78, models/densenet.py:73 */
@@ -60,7 +73,17 @@ typedef struct fpnmt_config {
   int32_t end_id;        /* tokenizer.word_index['<end>'],   pipeline.py:90                                      */
   int32_t true_beam;     /* 0 = reference init (all beams identical, pipeline.py:101-102); 1 = only beam 0 alive  */
   int32_t use_graphs;    /* 1 = replay the encode / decode-step programs as CUDA graphs                          */
-  int32_t reserved[8];
+  /* ---- the eight words below were `reserved[8]` in ABI 0.1; all-zero selects the defaults ---- */
+  int32_t kernel_opts;   /* FPNMT_OPT_* bit mask                                                                  */
+  int32_t cache_mode;    /* FPNMT_CACHE_*                                                                         */
+  int32_t decode_path;   /* FPNMT_DECODE_*                                                                        */
+  float length_penalty;  /* EXTENSION (not in the reference): alpha of the length normalisation applied when a beam
+                            finishes, score / ((5 + len) / 6)^alpha; 0 = reference ordering                        */
+  int32_t finished_beams;/* EXTENSION: 1 = a beam that emitted <end> is frozen and competes with its final score;
+                            the image stops when its best beam is a finished one.  0 = reference (pipeline.py:143-148:
+                            stop the moment the top beam emits <end>, finished lower beams keep decoding)          */
+  int32_t dec_groups;    /* DECODE_CHAIN only: cut the batch into this many concurrently decoded chains (0/1 = one) */
+  int32_t reserved[2];
 } fpnmt_config;
 
 typedef struct fpnmt_handle fpnmt_handle;

@@ -33,6 +33,18 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def _record_stages(bb, prec, table):
+    """Measured per-stage errors next to their bounds -> gpurun_out/parity_stages.json (summarised under profiles/)."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    p = os.path.join(d, "parity_stages.json")
+    data = json.load(open(p)) if os.path.exists(p) else {}
+    data["%s/%s" % (bb, prec)] = table
+    json.dump(data, open(p, "w"), indent=1, sort_keys=True)
+
+
 @pytest.fixture(scope="module", params=BACKBONES)
 def setup(request):
     bb = request.param
@@ -75,6 +87,8 @@ def test_encoder_stages(setup, prec, tol):
         assert tuple(feats[i].shape) == tuple(taps["features"][i].shape)
         check("features_api%d" % i, feats[i], taps["features"][i], emu["features"][i])
     eng.close()
+    print("%s %s stage rel-L2 (bound): " % (s["bb"], prec) + "  ".join("%s %.2e (%.2e)" % (k, errs[k], bound[k]) for k in errs))
+    _record_stages(s["bb"], prec, {k: {"err": errs[k], "bound": bound[k]} for k in errs})
     bad = {k: (v, bound[k]) for k, v in errs.items() if not v < bound[k]}
     assert not bad, (s["bb"], prec, bad)
 
@@ -224,13 +238,11 @@ def test_encoder_attention_mma_matches_simt_path():
     img = O.test_images(B, 512, seed=4)           # 512x512: the P3 view has 1024 keys (16 tiles of 64)
     outs = {}
     for mode in ("0", "1"):
-        os.environ["FPNMT_ENC_ATT_SIMT"] = mode
         eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16",
-                     use_graphs=False)
+                     use_graphs=False, opts=("enc_att_simt",) if mode == "1" else ())
         eng.encode(img.cuda())
         outs[mode] = [eng.tap("enc_layer%d" % l).cpu() for l in range(L)]
         eng.close()
-    os.environ.pop("FPNMT_ENC_ATT_SIMT", None)
     for l in range(L):
         assert rel(outs["0"][l], outs["1"][l]) < 2e-2, (l, rel(outs["0"][l], outs["1"][l]))
 
@@ -250,15 +262,13 @@ def test_fused_cross_attention_block_matches_unfused_path(size):
     gtok[:, 0] = 2
     outs = {}
     for mode in ("1", "0"):
-        os.environ["FPNMT_XATTN"] = mode
         eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=size, precision="bf16",
-                     use_graphs=False)
+                     use_graphs=False, decode_path="chain", opts=() if mode == "1" else ("no_xattn",))
         eng.encode(img.cuda())
         outs[mode] = eng.decode_logits(None, gtok.int().cuda()).cpu()
         ids, lens = eng.generate(img.cuda(), early_stop=False)
         outs["ids" + mode] = ids.clone()
         eng.close()
-    os.environ.pop("FPNMT_XATTN", None)
     err = rel(outs["1"], outs["0"])
     agree = float((outs["1"].argmax(-1) == outs["0"].argmax(-1)).float().mean())
     assert err < 5e-2 and agree >= 0.9, (size, err, agree)
@@ -290,18 +300,14 @@ def test_fused_cross_attention_other_beam_widths(beam):
     gtok = torch.randint(4, V, (3, T), generator=torch.Generator().manual_seed(6))
     gtok[:, 0] = 2
     outs = {}
-    try:
-        for mode in ("1", "0"):
-            os.environ["FPNMT_XATTN"] = mode
-            eng = Engine(w, backbone=bb, batch=3, beam=beam, vocab=V, max_len=T, num_layers=L, image_size=256,
-                         precision="bf16", use_graphs=False)
-            eng.encode(img.cuda())
-            outs[mode] = eng.decode_logits(None, gtok.int().cuda()).cpu()
-            ids, lens = eng.generate(img.cuda(), early_stop=False)
-            outs["ids" + mode] = ids
-            eng.close()
-    finally:
-        os.environ.pop("FPNMT_XATTN", None)
+    for mode in ("1", "0"):
+        eng = Engine(w, backbone=bb, batch=3, beam=beam, vocab=V, max_len=T, num_layers=L, image_size=256,
+                     precision="bf16", use_graphs=False, decode_path="chain", opts=() if mode == "1" else ("no_xattn",))
+        eng.encode(img.cuda())
+        outs[mode] = eng.decode_logits(None, gtok.int().cuda()).cpu()
+        ids, lens = eng.generate(img.cuda(), early_stop=False)
+        outs["ids" + mode] = ids
+        eng.close()
     assert rel(outs["1"], outs["0"]) < 5e-2
     assert (outs["ids1"] == outs["ids0"]).float().mean() >= 0.7
 
@@ -357,24 +363,20 @@ def test_double_buffered_host_input_matches_one_shot_generate():
 
 @pytest.mark.parametrize("groups", [2, 3])
 def test_decoder_groups_match_single_chain(groups):
-    """FPNMT_DEC_GROUPS cuts the batch into independent decode chains (parallel branches of the decode graph over row
+    """fpnmt_config.dec_groups (per-operator decode chain) cuts the batch into independent decode chains (parallel branches of the decode graph over row
     slices of the same buffers): identical ids, lengths and per-step scores as the single chain."""
     from fpnmt.engine import Engine
     bb = "mobilenet224_1.0"
     w = small_weights(bb, V, L, seed=8)
     img = O.test_images(5, S, seed=12).cuda()
     res = {}
-    try:
-        for g in (1, groups):
-            os.environ["FPNMT_DEC_GROUPS"] = str(g)
-            eng = Engine(w, backbone=bb, batch=5, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
-                         use_graphs=True)
-            res[g] = eng.generate(img, early_stop=False, return_scores=True)
-            again = eng.generate(img, early_stop=False)
-            assert torch.equal(again[0], res[g][0])
-            eng.close()
-    finally:
-        os.environ.pop("FPNMT_DEC_GROUPS", None)
+    for g in (1, groups):
+        eng = Engine(w, backbone=bb, batch=5, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
+                     use_graphs=True, decode_path="chain", dec_groups=g)
+        res[g] = eng.generate(img, early_stop=False, return_scores=True)
+        again = eng.generate(img, early_stop=False)
+        assert torch.equal(again[0], res[g][0])
+        eng.close()
     assert torch.equal(res[1][0], res[groups][0]) and torch.equal(res[1][1], res[groups][1])
     assert torch.allclose(res[1][2].cpu(), res[groups][2].cpu(), rtol=0, atol=0)
 
@@ -387,16 +389,12 @@ def test_fused_stem_matches_im2col_path(bb):
     w = small_weights(bb, V, L, seed=5)
     img = O.test_images(3, 512, seed=17).cuda()
     taps = {}
-    try:
-        for mode in ("1", "0"):
-            os.environ["FPNMT_STEM"] = mode
-            eng = Engine(w, backbone=bb, batch=3, beam=N, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16",
-                         use_graphs=False)
-            eng.encode(img)
-            taps[mode] = {n: eng.tap(n).cpu() for n in ("C3", "C5", "P3")}
-            eng.close()
-    finally:
-        os.environ.pop("FPNMT_STEM", None)
+    for mode in ("1", "0"):
+        eng = Engine(w, backbone=bb, batch=3, beam=N, vocab=V, max_len=T, num_layers=L, image_size=512, precision="bf16",
+                     use_graphs=False, opts=() if mode == "1" else ("no_stem",))
+        eng.encode(img)
+        taps[mode] = {n: eng.tap(n).cpu() for n in ("C3", "C5", "P3")}
+        eng.close()
     assert rel(taps["1"]["C3"], taps["0"]["C3"]) < 1e-2
     assert rel(taps["1"]["P3"], taps["0"]["P3"]) < 3e-2
     assert torch.isfinite(taps["1"]["C5"]).all()
@@ -479,3 +477,25 @@ def test_full_depth_resnet50_512_parity_bf16x3():
     ref_ids, ref_len = O.predict_batch_cached(mem_ref, Wv, Tf, Nf, 2, 3, num_layers=Lf)
     eng.close()
     assert (ids.numpy() == ref_ids).all() and (lens.numpy() == ref_len).all()
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """Opt-in shared-memory sizes are per-device function attributes: a second engine on another GPU of the
+    same process must launch every kernel (k_enc_attention_mma 66 KB, k_conv3x3_c1 57 KB, k_beam_step) and agree with
+    the first one bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from fpnmt.engine import Engine
+    bb = "mobilenet224_1.0"
+    w = small_weights(bb, V, L, seed=6)
+    img = O.test_images(B, S, seed=14)
+    outs = []
+    for dev in (1, 0):            # device 1 FIRST: a once-per-process guard would have armed device 0 only
+        with torch.cuda.device(dev):
+            eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
+                         device=dev)
+            ids, lens = eng.generate(img.to("cuda:%d" % dev), early_stop=False)
+            torch.cuda.synchronize(dev)
+            outs.append((ids.clone(), lens.clone()))
+            eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
