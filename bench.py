@@ -310,6 +310,7 @@ def run_own(args, wl):
     names = {"igemm": "igemm_kernel (tcgen05 implicit-GEMM convolutions / encoder projections)",
              "tgemm": "tgemm_kernel (tcgen05 skinny-row Dense layers of the decode step, LayerNorm fused)",
              "xattn": "xattn_kernel (tcgen05 fused decoder cross-attention block: Q-proj + attention + O-proj + residual + LayerNorm)",
+             "dstep": "dstep_kernel (cluster-stationary fused decoder: all layers + vocabulary projection + beam tail of a step, tcgen05)",
              "attention": "attention kernels (mma.sync encoder flash attention; decode self/cross attention)",
              "beam": "k_beam_step (softmax statistics + top-k over beam x vocab + beam bookkeeping)",
              "elementwise": "elementwise NHWC kernels (im2col, pooling, co-attention, LayerNorm, ...)"}
@@ -328,7 +329,7 @@ def run_own(args, wl):
     def family_entry(k):
         f = fam[k]
         per_launch_us = f["us"] / f["launches"]
-        tensor = k in ("igemm", "tgemm", "xattn")
+        tensor = k in ("igemm", "tgemm", "xattn", "dstep")
         # a kernel timed inside a long step: sustained bf16 peak; HBM peak for the bandwidth-bound families
         peak = peaks["tf_sustained"] if tensor else peaks["hbm_gbs"]
         ach = (f["flops"] / (f["us"] * 1e-6) / 1e12) if tensor else (f["bytes"] / (f["us"] * 1e-6) / 1e9)

@@ -901,6 +901,16 @@ int Engine::build_decoder() {
     RC(add_conv(dec_init_prog_, "dec_cross_kv", enc_out_, g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, ckv));
     taps_["cross_kv"] = ckv;
 
+    // Cluster-stationary fused decoder (dstep.cuh): one kernel per decode instead of 38 per step.  Needs the bf16 mode,
+    // log-domain scores and the reference beam semantics; everything else takes the per-operator chain below.
+    {
+      const int vslice = ((V + DS_CTAS - 1) / DS_CTAS + 127) / 128 * 128;
+      use_dstep_ = cfg_.decode_path == FPNMT_DECODE_AUTO && !split_ && cfg_.score_mode == FPNMT_SCORE_LOG && N <= 16 && D == 512 &&
+                   H == 8 && FF == 2048 && vslice / 128 <= DS_MAX_VTILES && n_base_ <= 16 && cfg_.cache_mode == FPNMT_CACHE_ANCESTRY &&
+                   !cfg_.finished_beams && cfg_.length_penalty == 0.f;
+      if (use_dstep_) return build_dstep(ckv, d_emb, d_pos);
+    }
+
     // Fused cross-attention block (bf16 mode): per-image folded operands, recomputed once per batch (xattn.cuh)
     const bool xattn = use_xattn_ && use_tgemm_ && !split_ && N <= XA_NROWS && n_base_ <= 16 && D == 512 && H == 8;
     bf16 *xMt = nullptr, *xNt = nullptr;
@@ -1049,6 +1059,11 @@ int Engine::build_decoder() {
         }
         RC(dense(ln + "_ffn1", out2, w.g1, ACT_LEAKY, hdn));
         RC(dense_res_ln(ln + "_ffn2+res", ln + "_ln3", hdn, w.g2, out2, w.lnp[4], w.lnp[5], out3));
+        if (Bg == B) {   // per-layer decoder states of the last executed step (parity taps, same names in the fused decoder)
+          taps_[ln + "_out1"] = out1;
+          taps_[ln + "_out2"] = out2;
+          taps_[ln + "_out3"] = out3;
+        }
         x = out3;
       }
       float* lg = logits_ + (size_t)r0 * V;
@@ -1107,6 +1122,170 @@ int Engine::build_decoder() {
         RC(build_chain(dg.b0, dg.Bg, dg.bs, dg.embed, dg.step, nullptr));
       }
     }
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------- fused decoder (dstep.cuh)
+// Appends one [rows x 64] bf16 tile image in the SWIZZLE_128B K-major shared-memory layout (row r at r*128 B, its 16-byte
+// chunk j at position j ^ (r & 7)): exactly what TMA would have written, so the kernel pulls it with a linear bulk copy.
+template <typename F>
+static void ds_pack_chunk(std::vector<uint16_t>& out, int rows, F get) {
+  const size_t base = out.size();
+  out.resize(base + (size_t)rows * 64);
+  for (int r = 0; r < rows; ++r)
+    for (int kk = 0; kk < 64; ++kk) out[base + (size_t)r * 64 + (((kk >> 3) ^ (r & 7)) << 3) + (kk & 7)] = f2bf(get(r, kk));
+}
+
+int Engine::build_dstep(const Tensor& ckv, const float* d_emb, const float* d_pos) {
+  const int B = cfg_.batch, N = cfg_.beam, L = cfg_.num_layers, V = cfg_.vocab, T = cfg_.max_len;
+  const int R = B * N;
+  DstepParams& p = dsp_;
+  p = DstepParams{};
+  p.B = B; p.N = N; p.R = R;
+  p.ipc = DS_ROWS / N;
+  p.L = L; p.T = T; p.V = V;
+  p.vslice = ((V + DS_CTAS - 1) / DS_CTAS + 127) / 128 * 128;
+  p.ntv = p.vslice / 128;
+  p.n_mem = n_base_;
+  const int clusters = (B + p.ipc - 1) / p.ipc;
+  // ---- weight streams
+  std::vector<uint16_t> ws;
+  ws.reserve(((size_t)L * DS_CTAS * DS_LAYER_STREAM + (size_t)DS_CTAS * p.ntv * 8 * 16384) / 2);
+  std::vector<float> lp((size_t)L * DSB_SIZE);
+  auto dense_w = [&](const std::string& name, int K, int F) -> const HostW* {
+    const HostW* k = W(name + "/kernel");
+    if (k && (k->shape.size() != 2 || k->shape[0] != K || k->shape[1] != F)) {
+      set_last_error(name + "/kernel: expected shape (" + std::to_string(K) + ", " + std::to_string(F) + ")");
+      return nullptr;
+    }
+    return k;
+  };
+  auto copy_vec = [&](const std::string& key, float* dst, int n) -> int {
+    const HostW* v = W(key);
+    if (!v) return FPNMT_ERR_MISSING;
+    if ((int)v->data.size() != n) return fail(FPNMT_ERR_INVALID, key + ": expected " + std::to_string(n) + " elements");
+    std::copy(v->data.begin(), v->data.end(), dst);
+    return 0;
+  };
+  for (int l = 0; l < L; ++l) {
+    const std::string d = std::string(TR) + "/decoder/dec_layers/" + std::to_string(l);
+    const HostW *wq = dense_w(d + "/mha1/wq", 512, 512), *wk = dense_w(d + "/mha1/wk", 512, 512), *wv = dense_w(d + "/mha1/wv", 512, 512),
+                *wo1 = dense_w(d + "/mha1/dense", 512, 512), *wq2 = dense_w(d + "/mha2/wq", 512, 512),
+                *wo2 = dense_w(d + "/mha2/dense", 512, 512), *w1 = dense_w(d + "/ffn1", 512, 2048), *w2 = dense_w(d + "/ffn2", 2048, 512);
+    if (!wq || !wk || !wv || !wo1 || !wq2 || !wo2 || !w1 || !w2) return FPNMT_ERR_MISSING;
+    for (int c = 0; c < DS_CTAS; ++c) {
+      const size_t before = ws.size();
+      for (int kc = 0; kc < 8; ++kc)
+        ds_pack_chunk(ws, 128, [&](int r, int kk) {
+          return r < 64 ? wq->data[(size_t)(kc * 64 + kk) * 512 + c * 64 + r] : wk->data[(size_t)(kc * 64 + kk) * 512 + c * 64 + r - 64];
+        });
+      for (const HostW* m : {wv, wo1, wq2, wo2})
+        for (int kc = 0; kc < 8; ++kc)
+          ds_pack_chunk(ws, 64, [&](int r, int kk) { return m->data[(size_t)(kc * 64 + kk) * 512 + c * 64 + r]; });
+      for (int ft = 0; ft < 2; ++ft)
+        for (int kc = 0; kc < 8; ++kc)
+          ds_pack_chunk(ws, 128, [&](int r, int kk) { return w1->data[(size_t)(kc * 64 + kk) * 2048 + c * 256 + ft * 128 + r]; });
+      for (int ft = 0; ft < 4; ++ft)
+        for (int kc = 0; kc < 4; ++kc)
+          ds_pack_chunk(ws, 128, [&](int r, int kk) { return w2->data[(size_t)(c * 256 + kc * 64 + kk) * 512 + ft * 128 + r]; });
+      if ((ws.size() - before) * 2 != DS_LAYER_STREAM) return fail(FPNMT_ERR_INVALID, "build_dstep: layer stream size mismatch");
+    }
+    float* q = lp.data() + (size_t)l * DSB_SIZE;
+    RC(copy_vec(d + "/mha1/wq/bias", q + DSB_Q, 512));
+    RC(copy_vec(d + "/mha1/wk/bias", q + DSB_K, 512));
+    RC(copy_vec(d + "/mha1/wv/bias", q + DSB_V, 512));
+    RC(copy_vec(d + "/mha1/dense/bias", q + DSB_O1, 512));
+    RC(copy_vec(d + "/mha2/wq/bias", q + DSB_Q2, 512));
+    RC(copy_vec(d + "/mha2/dense/bias", q + DSB_O2, 512));
+    RC(copy_vec(d + "/ffn1/bias", q + DSB_F1, 2048));
+    RC(copy_vec(d + "/ffn2/bias", q + DSB_F2, 512));
+    RC(copy_vec(d + "/layernorm1/gamma", q + DSB_LN1G, 512));
+    RC(copy_vec(d + "/layernorm1/beta", q + DSB_LN1B, 512));
+    RC(copy_vec(d + "/layernorm2/gamma", q + DSB_LN2G, 512));
+    RC(copy_vec(d + "/layernorm2/beta", q + DSB_LN2B, 512));
+    RC(copy_vec(d + "/layernorm3/gamma", q + DSB_LN3G, 512));
+    RC(copy_vec(d + "/layernorm3/beta", q + DSB_LN3B, 512));
+  }
+  p.final_off = ws.size() * 2;
+  {
+    const HostW* wf = dense_w(std::string(TR) + "/final_layer", 512, V);
+    const HostW* bf = W(std::string(TR) + "/final_layer/bias");
+    if (!wf || !bf) return FPNMT_ERR_MISSING;
+    if ((int)bf->data.size() != V) return fail(FPNMT_ERR_INVALID, "final_layer/bias: expected vocab elements");
+    for (int c = 0; c < DS_CTAS; ++c)
+      for (int vt = 0; vt < p.ntv; ++vt)
+        for (int kc = 0; kc < 8; ++kc)
+          ds_pack_chunk(ws, 128, [&](int r, int kk) {
+            const int f = c * p.vslice + vt * 128 + r;
+            return f < V ? wf->data[(size_t)(kc * 64 + kk) * V + f] : 0.f;
+          });
+    std::vector<float> vb((size_t)DS_CTAS * p.vslice, 0.f);
+    std::copy(bf->data.begin(), bf->data.end(), vb.begin());
+    float* dvb;
+    RC(upload_f32(vb, &dvb));
+    p.vbias = dvb;
+  }
+  uint8_t* dws = (uint8_t*)dalloc(ws.size() * 2);
+  if (!dws) return FPNMT_ERR_CUDA;
+  FPNMT_CUDA_OK(cudaMemcpy(dws, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
+  p.wstream = dws;
+  float* dlp;
+  RC(upload_f32(lp, &dlp));
+  p.lparams = dlp;
+  p.emb = d_emb;
+  p.pos = d_pos;
+  {
+    const HostW* e = W(std::string(TR) + "/decoder/embedding/embeddings");
+    if (!e || e->shape.size() != 2 || e->shape[0] < V || e->shape[1] != 512)
+      return fail(FPNMT_ERR_INVALID, "decoder/embedding/embeddings: expected shape (>= vocab, 512)");
+  }
+  // ---- caches, exchange buffers
+  const size_t cache_elems = (size_t)L * R * T * 512;
+  p.kcache = (bf16*)dalloc(cache_elems * 2);
+  p.vcache = (bf16*)dalloc(cache_elems * 2);
+  p.ckv = ckv.a.p;
+  p.ckv_ld = ckv.a.ld;
+  const size_t xr = (size_t)clusters * 32;
+  p.x_att = (bf16*)dalloc(xr * 512 * 2);
+  p.x_pre = (float*)dalloc(xr * 512 * 4);
+  p.x_part = (float*)dalloc((size_t)clusters * DS_CTAS * 32 * 512 * 4);
+  p.x_stat = (float*)dalloc(xr * DS_CTAS * 2 * 4);
+  p.x_cval = (float*)dalloc(xr * DS_CTAS * N * 4);
+  p.x_cidx = (int*)dalloc(xr * DS_CTAS * N * 4);
+  if (!p.kcache || !p.vcache || !p.x_att || !p.x_pre || !p.x_part || !p.x_stat || !p.x_cval || !p.x_cidx) return FPNMT_ERR_CUDA;
+  FPNMT_CUDA_OK(cudaMemset(p.x_att, 0, xr * 512 * 2));
+  FPNMT_CUDA_OK(cudaMemset(p.x_pre, 0, xr * 512 * 4));
+  p.logits_out = logits_;
+  p.ld_logits = V;
+  if (cfg_.kernel_opts & FPNMT_OPT_DSTEP_TAPS) {   // LayerNorm outputs of every layer (last executed step), for the parity tests
+    float* dbg = (float*)dalloc((size_t)L * 3 * xr * 512 * 4);
+    if (!dbg) return FPNMT_ERR_CUDA;
+    FPNMT_CUDA_OK(cudaMemset(dbg, 0, (size_t)L * 3 * xr * 512 * 4));
+    p.dbg = dbg;
+    for (int l = 0; l < L; ++l)
+      for (int i = 0; i < 3; ++i)
+        taps_f32_["dec" + std::to_string(l) + "_out" + std::to_string(i + 1)] = F32Tap{dbg + (size_t)(l * 3 + i) * xr * 512, xr * 512};
+  }
+  p.st = bs_;
+  p.mode = 0;
+  RC(dstep_set_attributes());
+  // one-step op for the per-op profiler (the product decode is ONE launch of all steps)
+  {
+    Op o;
+    o.name = "dstep(all layers + vocabulary projection + beam tail of one step)";
+    o.kind = "dstep";
+    o.flops = 2.0 * R * ((double)L * (512.0 * 1536 + 3.0 * 512 * 512 + 2.0 * 512 * 2048) + 512.0 * V);
+    o.bytes = (double)ws.size() * 2 + (double)L * R * (T / 2) * 2 * 512 * 2;   // weight streams once + K/V cache at t = T/2
+    o.idempotent = false;
+    o.run = [this](cudaStream_t s) {
+      DstepParams q = dsp_;
+      q.t0 = prof_t_;
+      q.nsteps = 1;
+      if (prof_t_ + 1 < cfg_.max_len) ++prof_t_;
+      return dstep_launch(q, s);
+    };
+    step_prog_.push_back(std::move(o));
   }
   return 0;
 }
@@ -1246,7 +1425,17 @@ int Engine::features(const float* images, int on_host, float* const out5[5], cud
   return 0;
 }
 
+int Engine::get_tap_f32(const std::string& name, float* out, size_t cap, size_t* count, cudaStream_t s) {
+  const F32Tap& t = taps_f32_[name];
+  if (count) *count = t.count;
+  if (!out) return 0;
+  if (cap < t.count) return fail(FPNMT_ERR_INVALID, "get_tap: buffer too small");
+  FPNMT_CUDA_OK(cudaMemcpyAsync(out, t.p, t.count * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
 int Engine::get_tap(const char* name, float* out, size_t cap, size_t* count, cudaStream_t s) {
+  if (taps_f32_.count(name)) return get_tap_f32(name, out, cap, count, s);
   auto it = taps_.find(name);
   if (it == taps_.end()) return fail(FPNMT_ERR_INVALID, std::string("unknown tap: ") + name);
   const Tensor& t = it->second;
@@ -1292,7 +1481,16 @@ int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, flo
   k_forced_init<<<(R + 255) / 256, 256, 0, s>>>(bs_, tokens, t);
   FPNMT_CUDA_OK(cudaGetLastError());
   for (int i = 0; i < t; ++i) {
-    RC(run_program(step_forced_prog_, s));
+    if (use_dstep_) {   // fused decoder, teacher-forcing mode: one step, fp32 logits of every row written out
+      DstepParams q = dsp_;
+      q.t0 = i;
+      q.nsteps = 1;
+      q.mode = 1;
+      RC(dstep_launch(q, s));
+      launches += 1;
+    } else {
+      RC(run_program(step_forced_prog_, s));
+    }
     k_forced_tail<<<cfg_.batch, 256, 0, s>>>(bs_, logits_, tokens, t, logits_out);
     k_step_inc<<<1, 1, 0, s>>>(bs_.step);
     FPNMT_CUDA_OK(cudaGetLastError());
@@ -1320,7 +1518,26 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
   if (!finalized_) return fail(FPNMT_ERR_STATE, "decode before finalize_weights");
   FPNMT_CUDA_OK(cudaSetDevice(dev_));
   const int B = cfg_.batch, T = cfg_.max_len;
-  if (cfg_.use_graphs && !early_stop && groups_.size() > 1) {
+  if (use_dstep_) {
+    // Fused decoder: the whole fixed-length decode is ONE launch (every cluster runs its images through all T steps on
+    // its own); with early stop the host looks at the finished-image counter every 4 steps, as the chain path does.
+    RC(launch_beam_init(bs_, cfg_.true_beam, s));
+    launches += 1;
+    RC(run_program(dec_init_prog_, s));
+    DstepParams q = dsp_;
+    const int chunk = early_stop ? 4 : T;
+    for (int t0 = 0; t0 < T; t0 += chunk) {
+      q.t0 = t0;
+      q.nsteps = std::min(chunk, T - t0);
+      RC(dstep_launch(q, s));
+      launches += 1;
+      if (early_stop && t0 + chunk < T) {
+        FPNMT_CUDA_OK(cudaMemcpyAsync(h_pinned_, bs_.n_done, 4, cudaMemcpyDeviceToHost, s));
+        FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+        if (h_pinned_[0] >= B) break;
+      }
+    }
+  } else if (cfg_.use_graphs && !early_stop && groups_.size() > 1) {
     // fixed-length decode with decoder groups: ONE graph = fork -> per group (step-0 embedding, T steps) -> join
     RC(launch_beam_init(bs_, cfg_.true_beam, s));            // whole-batch state (outputs, flags) ...
     for (auto& g : groups_) RC(launch_beam_init(g.bs, cfg_.true_beam, s));   // ... and every group's own step counters
@@ -1459,6 +1676,7 @@ int Engine::profile(int iters, char* buf, size_t cap) {
   RC(run_program(dec_init_prog_, s));
   RC(run_program(embed_prog_, s));
   const int warm = cfg_.max_len / 2;
+  prof_t_ = 0;
   for (int t = 0; t < warm; ++t) RC(run_program(step_prog_, s));
   RC(profile_program(dec_init_prog_, iters, json, "decode_init"));
   json += ", ";

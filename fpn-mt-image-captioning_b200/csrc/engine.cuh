@@ -13,6 +13,7 @@
 #include "tgemm.cuh"
 #include "stem.cuh"
 #include "xattn.cuh"
+#include "dstep.cuh"
 
 namespace fpnmt {
 
@@ -67,6 +68,8 @@ class Engine {
                float* step_scores, cudaStream_t s);
   int profile(int iters, char* buf, size_t cap);
   int capture_groups(int T);
+  int build_dstep(const Tensor& ckv, const float* d_emb, const float* d_pos);
+  int get_tap_f32(const std::string& name, float* out, size_t cap, size_t* count, cudaStream_t s);
   int add_stem(Program& p, const std::string& name, int kh, int pad, int cout, const GemmW& gw, int Kp, int act, const Tensor& out);
   // double-buffered host input: copy batch i+1 on the engine's copy stream while batch i runs
   int stage_images(const float* host_images, int slot);
@@ -107,6 +110,11 @@ class Engine {
   Tensor enc_out_;                        // (B*16, 512)
   int n_base_ = 16;                       // tokens of the baseline view
   BeamState bs_{};
+  bool use_dstep_ = false;                // cluster-stationary fused decoder (dstep.cuh) instead of the per-operator chain
+  DstepParams dsp_{};
+  int prof_t_ = 0;                        // step index used by the single-step op of the fused decoder in profile()
+  struct F32Tap { const float* p; size_t count; };
+  std::map<std::string, F32Tap> taps_f32_;
   float* logits_ = nullptr;               // [rows][V]
   int* forced_tokens_ = nullptr;          // [B][T] teacher-forced tokens
   int* forced_len_ = nullptr;

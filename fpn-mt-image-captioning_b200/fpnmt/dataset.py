@@ -46,24 +46,69 @@ def load_image(img_path: str, caption=None):
     return preprocess_input(arr), caption
 
 
+KERAS_DEFAULT_FILTERS = '!"#$%&()*+,-./:;<=>?@[\\]^_`{|}~\t\n'
+REFERENCE_FILTERS = '!"#$%&()*+-/:;=?@[\\]^_`{|}~ '      # dataset.py:60 (keeps '.', ',', '<', '>')
+
+
 class Tokenizer:
-    """The subset of keras.preprocessing.text.Tokenizer the hot path uses (pipeline.py:19,89-90,169,188)."""
+    """The part of keras.preprocessing.text.Tokenizer the hot path uses (pipeline.py:19,89-90,169,188), with Keras'
+    semantics for the two constructor arguments the reference sets (dataset.py:58-60, restored from the JSON config by
+    dataset.py:113): an id >= `num_words`, and an id that is not in `index_word` while `oov_token` is set, both print the
+    OOV word; without an OOV token such ids are dropped.  Pinned by tests/golden/tokenizer_golden.json, a file written by
+    the reference's own `store_tokenizer_to_path`."""
 
     def __init__(self, word_index: Dict[str, int], index_word: Optional[Dict[int, str]] = None, config: Optional[dict] = None,
                  word_counts: Optional[dict] = None, word_docs: Optional[dict] = None, index_docs: Optional[dict] = None):
         self.word_index = dict(word_index)
         self.index_word = dict(index_word) if index_word is not None else {i: w for w, i in self.word_index.items()}
-        self.config = config or {}
+        self.config = dict(config or {})
+        self.num_words = self.config.get("num_words")
+        self.oov_token = self.config.get("oov_token")
+        self.filters = self.config.get("filters", KERAS_DEFAULT_FILTERS)
+        self.lower = self.config.get("lower", True)
+        self.split = self.config.get("split", " ")
         self.word_counts, self.word_docs, self.index_docs = word_counts or {}, word_docs or {}, index_docs or {}
 
+    def _words(self, text: str) -> List[str]:
+        if self.lower:
+            text = text.lower()
+        text = text.translate(str.maketrans({c: self.split for c in self.filters}))
+        return [w for w in text.split(self.split) if w]
+
+    def texts_to_sequences(self, texts: Iterable[str]) -> List[List[int]]:
+        oov = self.word_index.get(self.oov_token)
+        out = []
+        for text in texts:
+            vect = []
+            for w in self._words(text):
+                i = self.word_index.get(w)
+                if i is not None:
+                    if self.num_words and i >= self.num_words:
+                        if oov is not None:
+                            vect.append(oov)
+                    else:
+                        vect.append(i)
+                elif self.oov_token is not None:
+                    vect.append(oov)
+            out.append(vect)
+        return out
+
     def sequences_to_texts(self, sequences: Iterable[Iterable[int]]) -> List[str]:
+        oov = self.word_index.get(self.oov_token)
         out = []
         for seq in sequences:
             words = []
             for i in seq:
-                w = self.index_word.get(int(i))
-                if w is not None:          # Keras skips indices it does not know (0 = padding)
-                    words.append(w)
+                i = int(i)
+                w = self.index_word.get(i)
+                if w is not None:
+                    if self.num_words and i >= self.num_words:
+                        if oov is not None:
+                            words.append(self.index_word[oov])
+                    else:
+                        words.append(w)
+                elif self.oov_token is not None:
+                    words.append(self.index_word[oov])
             out.append(" ".join(words))
         return out
 
@@ -78,13 +123,17 @@ class Tokenizer:
 
     @classmethod
     def synthetic(cls, vocab: int) -> "Tokenizer":
-        """Vocabulary for synthetic runs: pad=0 (no word), <unk>=1, <start>=2, <end>=3, w4..w{V-1}."""
-        wi = {"<unk>": C.UNK_ID, "<start>": C.START_ID, "<end>": C.END_ID}
+        """Vocabulary for synthetic runs, shaped like the reference's (dataset.py:58-65): '' = 0 (padding), the OOV word
+        "unk" = 1, <start> = 2, <end> = 3, w4..w{V-1}; num_words = TOP_K, oov_token = "unk"."""
+        wi = {"unk": C.UNK_ID, "<start>": C.START_ID, "<end>": C.END_ID}
         for i in range(4, vocab):
             wi["w%d" % i] = i
         iw = {i: w for w, i in wi.items()}
-        iw[C.PAD_ID] = "<pad>"               # dataset.py:62,67-68 adds index 0 = '<pad>' to index_word
-        return cls(wi, iw)
+        wi[""] = C.PAD_ID                    # dataset.py:64-65
+        iw[C.PAD_ID] = ""
+        cfg = {"num_words": C.TOP_K, "filters": REFERENCE_FILTERS, "lower": True, "split": " ", "char_level": False,
+               "oov_token": "unk", "document_count": 0}
+        return cls(wi, iw, cfg)
 
 
 def _tokenizer_from_json(json_string: str) -> Tokenizer:

@@ -242,8 +242,42 @@ def load_image_golden(out: dict):
     out["load_image_out2_sub"] = np.asarray(res2).astype(np.float32)[::7, ::5].copy()
 
 
+def tokenizer_golden():
+    """Tokenizer wire format and detokenisation, written and read back by the reference's OWN dataset.py functions
+    (`store_tokenizer_to_path` :137-146, `load_tokenizer_from_path` / `_tokenizer_from_json` :96-135) around the Keras
+    Tokenizer (shim restatement).  The tokenizer is built exactly as dataset.py:58-68 does (num_words, oov_token="unk", the
+    reference's filter string, '' added as index 0), with a SMALL num_words so that ids >= num_words exist.  Outputs:
+    tests/golden/tokenizer_golden.json (the file the reference writes) and tokenizer_expect.json (sequences -> texts)."""
+    import json
+    import re
+    import dataset as D   # reference module
+    caps = ["the heart is normal in size .", "no acute cardiopulmonary abnormality .", "the lungs are clear , no effusion .",
+            "heart size is normal . the lungs are clear .", "no pneumothorax or pleural effusion is seen .",
+            "stable cardiomegaly , mild edema .", "the mediastinum is normal .", "no focal consolidation ."]
+    captions = ["<start> " + c + " <end>" for c in caps]                                              # dataset.py:52
+    tokenizer = tf.keras.preprocessing.text.Tokenizer(num_words=24, oov_token="unk",
+                                                      filters='!"#$%&()*+-/:;=?@[\\]^_`{|}~ ')           # dataset.py:58-60
+    tokenizer.fit_on_texts(captions)                                                                  # :61
+    tokenizer.word_index[''] = 0                                                                      # :64
+    tokenizer.index_word[0] = ''                                                                      # :65
+    path = os.path.join(HERE, "tokenizer_golden.json")
+    D.store_tokenizer_to_path(tokenizer, path)                                                        # :67
+    tok2 = D.load_tokenizer_from_path(path)
+    captions2 = [re.sub(r'([.,])', r" \1 ", c) for c in captions]                                     # :70
+    seqs = tok2.texts_to_sequences(captions2)                                                         # :73
+    probes = seqs[:4] + [[2, 5, 23, 24, 25, 30, 3], [0, 0, 7, 999, 1], [len(tok2.index_word) - 1, 4, 0], []]
+    expect = {"num_words": tok2.num_words, "oov_token": tok2.oov_token, "vocab_size": len(tok2.index_word),
+              "start_id": tok2.word_index["<start>"], "end_id": tok2.word_index["<end>"],
+              "sequences": probes, "texts": tok2.sequences_to_texts(probes),
+              "captions": captions2[:4], "caption_sequences": seqs[:4]}
+    with open(os.path.join(HERE, "tokenizer_expect.json"), "w") as f:
+        json.dump(expect, f, indent=1)
+    print("tokenizer golden: vocab", expect["vocab_size"], "start", expect["start_id"], "end", expect["end_id"])
+
+
 def main():
     unit, model = {}, {}
+    tokenizer_golden()
     unit_goldens(unit)
     load_image_golden(unit)
     np.savez_compressed(os.path.join(HERE, "reference_units.npz"), **unit)

@@ -742,11 +742,91 @@ class _Anything:
 
 
 class _Tokenizer:
-    def __init__(self, **cfg):
+    """tf.keras.preprocessing.text.Tokenizer == keras_preprocessing.text.Tokenizer (third-party, un-vendored; the TF 2.0/2.1
+    the reference targets bundles keras-preprocessing 1.1.0).  Restated from its published algorithm: fit_on_texts,
+    texts_to_sequences, sequences_to_texts (num_words / oov_token semantics), get_config / to_json."""
+
+    def __init__(self, num_words=None, filters='!"#$%&()*+,-./:;<=>?@[\\]^_`{|}~\t\n', lower=True, split=" ", char_level=False,
+                 oov_token=None, document_count=0, **kwargs):
+        import collections
+        self.word_counts = collections.OrderedDict()
+        self.word_docs = collections.defaultdict(int)
+        self.filters, self.split, self.lower, self.num_words = filters, split, lower, num_words
+        self.document_count, self.char_level, self.oov_token = document_count, char_level, oov_token
+        self.index_docs = collections.defaultdict(int)
         self.word_index, self.index_word = {}, {}
 
-    def sequences_to_texts(self, seqs):
-        return [" ".join(self.index_word[int(i)] for i in s if int(i) in self.index_word) for s in seqs]
+    def _words(self, text):
+        if self.lower:
+            text = text.lower()
+        text = text.translate(str.maketrans({c: self.split for c in self.filters}))
+        return [w for w in text.split(self.split) if w]
+
+    def fit_on_texts(self, texts):
+        for text in texts:
+            self.document_count += 1
+            seq = self._words(text)
+            for w in seq:
+                self.word_counts[w] = self.word_counts.get(w, 0) + 1
+            for w in set(seq):
+                self.word_docs[w] += 1
+        wcounts = list(self.word_counts.items())
+        wcounts.sort(key=lambda x: x[1], reverse=True)
+        sorted_voc = [] if self.oov_token is None else [self.oov_token]
+        sorted_voc.extend(wc[0] for wc in wcounts)
+        import builtins
+        self.word_index = dict(zip(sorted_voc, list(builtins.range(1, len(sorted_voc) + 1))))   # index 0 is reserved
+        self.index_word = {c: w for w, c in self.word_index.items()}
+        for w, c in list(self.word_docs.items()):
+            self.index_docs[self.word_index[w]] = c
+
+    def texts_to_sequences(self, texts):
+        num_words, oov = self.num_words, self.word_index.get(self.oov_token)
+        out = []
+        for text in texts:
+            vect = []
+            for w in self._words(text):
+                i = self.word_index.get(w)
+                if i is not None:
+                    if num_words and i >= num_words:
+                        if oov is not None:
+                            vect.append(oov)
+                    else:
+                        vect.append(i)
+                elif self.oov_token is not None:
+                    vect.append(oov)
+            out.append(vect)
+        return out
+
+    def sequences_to_texts(self, sequences):
+        num_words, oov = self.num_words, self.word_index.get(self.oov_token)
+        out = []
+        for seq in sequences:
+            vect = []
+            for num in seq:
+                word = self.index_word.get(num)
+                if word is not None:
+                    if num_words and num >= num_words:
+                        if oov is not None:
+                            vect.append(self.index_word[oov])
+                    else:
+                        vect.append(word)
+                elif self.oov_token is not None:
+                    vect.append(self.index_word[oov])
+            out.append(" ".join(vect))
+        return out
+
+    def get_config(self):
+        import json
+        return {"num_words": self.num_words, "filters": self.filters, "lower": self.lower, "split": self.split,
+                "char_level": self.char_level, "oov_token": self.oov_token, "document_count": self.document_count,
+                "word_counts": json.dumps(self.word_counts), "word_docs": json.dumps(self.word_docs),
+                "index_docs": json.dumps(self.index_docs), "index_word": json.dumps(self.index_word),
+                "word_index": json.dumps(self.word_index)}
+
+    def to_json(self, **kwargs):
+        import json
+        return json.dumps({"class_name": self.__class__.__name__, "config": self.get_config()}, **kwargs)
 
 
 def _mobilenet_v2(input_tensor=None, alpha=1.0, include_top=False, pooling=None, weights=None, **kw):

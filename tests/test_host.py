@@ -116,8 +116,27 @@ def test_tokenizer_roundtrip_double_encoded_json(tmp_path):
     t2 = load_tokenizer_from_path(p)
     assert t2.word_index == tok.word_index and t2.index_word == tok.index_word
     assert t2.word_index["<start>"] == 2 and t2.word_index["<end>"] == 3 and len(t2.index_word) == 40
-    assert t2.sequences_to_texts([[5, 6, 0, 7]]) == ["w5 w6 <pad> w7"]
-    assert t2.sequences_to_texts([[5, 999]]) == ["w5"]         # unknown indices are skipped like Keras
+    assert t2.num_words == 10000 and t2.oov_token == "unk"     # restored from the JSON config (dataset.py:113)
+    assert t2.sequences_to_texts([[5, 6, 0, 7]]) == ["w5 w6  w7"]      # padding id 0 is the empty word (dataset.py:64-65)
+    assert t2.sequences_to_texts([[5, 999]]) == ["w5 unk"]     # Keras: unknown ids print the OOV word when oov_token is set
+    no_oov = Tokenizer({"a": 1, "b": 2})
+    assert no_oov.sequences_to_texts([[1, 7, 2]]) == ["a b"]   # ... and are dropped when it is not
+
+
+def test_tokenizer_matches_file_and_texts_written_by_the_reference():
+    """tests/golden/tokenizer_golden.json was written by the reference's own store_tokenizer_to_path (dataset.py:137-146)
+    from a Keras Tokenizer built as dataset.py:58-65 does (make_golden.py::tokenizer_golden); tokenizer_expect.json holds
+    what that tokenizer answers.  ids >= num_words and ids missing from index_word must print the OOV word."""
+    from fpnmt.dataset import load_tokenizer_from_path
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    tok = load_tokenizer_from_path(os.path.join(g, "tokenizer_golden.json"))
+    exp = json.load(open(os.path.join(g, "tokenizer_expect.json")))
+    assert tok.num_words == exp["num_words"] and tok.oov_token == exp["oov_token"]
+    assert len(tok.index_word) == exp["vocab_size"]                                # pipeline.py:19 target_vocab_size
+    assert tok.word_index["<start>"] == exp["start_id"] and tok.word_index["<end>"] == exp["end_id"]   # pipeline.py:89-90
+    assert tok.sequences_to_texts(exp["sequences"]) == exp["texts"]
+    assert tok.texts_to_sequences(exp["captions"]) == exp["caption_sequences"]
+    assert any("unk" in t for t in exp["texts"])                                   # the fixture does exercise the OOV paths
 
 
 def test_load_image_contract(tmp_path):
