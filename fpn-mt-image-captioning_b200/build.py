@@ -33,9 +33,12 @@ def _stamp() -> str:
 
 
 def build(force: bool = False, verbose: bool = True, dbg_stamps: bool = False) -> str:
-    if dbg_stamps:    # developer build: globaltimer timelines inside the tcgen05 kernels (FPNMT_DBG_OP=<op name>)
-        FLAGS.append("-DFPNMT_DBG_STAMPS")
+    global OUT
     bdir = os.path.join(CSRC, "build")
+    if dbg_stamps:    # developer build -> libfpnmt_dbg.so: globaltimer timelines inside the kernels (FPNMT_DBG_OP=<op name>);
+        FLAGS.append("-DFPNMT_DBG_STAMPS")      # load it by setting fpnmt._lib.LIB_PATH before the first Engine
+        OUT = os.path.join(HERE, "libfpnmt_dbg.so")
+        bdir = os.path.join(CSRC, "build_dbg")
     os.makedirs(bdir, exist_ok=True)
     stamp_file = os.path.join(bdir, "stamp")
     stamp = _stamp()

@@ -84,7 +84,7 @@ int Engine::init() {
   use_stem_ = !(c.kernel_opts & FPNMT_OPT_NO_STEM);
   use_tgemm_ = !(c.kernel_opts & FPNMT_OPT_NO_TGEMM);
   set_pdl_mode((c.kernel_opts & FPNMT_OPT_NO_PDL) ? 0 : (c.kernel_opts & FPNMT_OPT_PDL_GEMM_ONLY) ? 2 : 1);
-  if (c.cache_mode < 0 || c.cache_mode > 1 || c.decode_path < 0 || c.decode_path > 1 || c.dec_groups < 0 || c.length_penalty < 0.f)
+  if (c.cache_mode < 0 || c.cache_mode > 1 || c.decode_path < 0 || c.decode_path > 2 || c.dec_groups < 0 || c.length_penalty < 0.f)
     return fail(FPNMT_ERR_INVALID, "bad cache_mode / decode_path / dec_groups / length_penalty");
   FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
   FPNMT_CUDA_OK(cudaMallocHost(&h_pinned_, 64));
@@ -97,8 +97,8 @@ long long* Engine::dbg_timeline(const std::string& name) {
 #ifdef FPNMT_DBG_STAMPS
   const char* dn = getenv("FPNMT_DBG_OP");
   if (dn && name == dn) {
-    dbg_buf_ = (long long*)dalloc(16 * 9 * sizeof(long long));
-    if (dbg_buf_) cudaMemset(dbg_buf_, 0, 16 * 9 * sizeof(long long));
+    dbg_buf_ = (long long*)dalloc(192 * sizeof(long long));
+    if (dbg_buf_) cudaMemset(dbg_buf_, 0, 192 * sizeof(long long));
     return dbg_buf_;
   }
 #endif
@@ -901,13 +901,17 @@ int Engine::build_decoder() {
     RC(add_conv(dec_init_prog_, "dec_cross_kv", enc_out_, g, 1, 1, 0, 0, ACT_NONE, RES_NONE, nullptr, ckv));
     taps_["cross_kv"] = ckv;
 
-    // Cluster-stationary fused decoder (dstep.cuh): one kernel per decode instead of 38 per step.  Needs the bf16 mode,
+    // Group-stationary fused decoder (dstep.cuh): one kernel per decode instead of 38 per step.  Needs the bf16 mode,
     // log-domain scores and the reference beam semantics; everything else takes the per-operator chain below.
     {
       const int vslice = ((V + DS_CTAS - 1) / DS_CTAS + 127) / 128 * 128;
-      use_dstep_ = cfg_.decode_path == FPNMT_DECODE_AUTO && !split_ && cfg_.score_mode == FPNMT_SCORE_LOG && N <= 16 && D == 512 &&
+      const bool want = cfg_.decode_path == FPNMT_DECODE_FUSED;
+      use_dstep_ = want && !split_ && cfg_.score_mode == FPNMT_SCORE_LOG && N <= 16 && D == 512 &&
                    H == 8 && FF == 2048 && vslice / 128 <= DS_MAX_VTILES && n_base_ <= 16 && cfg_.cache_mode == FPNMT_CACHE_ANCESTRY &&
                    !cfg_.finished_beams && cfg_.length_penalty == 0.f;
+      if (want && !use_dstep_)
+        return fail(FPNMT_ERR_INVALID, "decode_path FUSED needs precision bf16, score_mode log, beam <= 16, dff 2048, vocab <= 14336, "
+                                       "cache_mode ancestry and the reference beam semantics");
       if (use_dstep_) return build_dstep(ckv, d_emb, d_pos);
     }
 
@@ -1127,14 +1131,14 @@ int Engine::build_decoder() {
 }
 
 // --------------------------------------------------------------------------------------------- fused decoder (dstep.cuh)
-// Appends one [rows x 64] bf16 tile image in the SWIZZLE_128B K-major shared-memory layout (row r at r*128 B, its 16-byte
-// chunk j at position j ^ (r & 7)): exactly what TMA would have written, so the kernel pulls it with a linear bulk copy.
+// Appends one [rows x 64] bf16 tile (row r = 128 contiguous bytes) to the weight stream; the kernel pulls 128-row boxes of
+// the stream with TMA (SWIZZLE_128B), so consecutive tiles form the exact consumption order of one CTA.
 template <typename F>
 static void ds_pack_chunk(std::vector<uint16_t>& out, int rows, F get) {
   const size_t base = out.size();
   out.resize(base + (size_t)rows * 64);
   for (int r = 0; r < rows; ++r)
-    for (int kk = 0; kk < 64; ++kk) out[base + (size_t)r * 64 + (((kk >> 3) ^ (r & 7)) << 3) + (kk & 7)] = f2bf(get(r, kk));
+    for (int kk = 0; kk < 64; ++kk) out[base + (size_t)r * 64 + kk] = f2bf(get(r, kk));
 }
 
 int Engine::build_dstep(const Tensor& ckv, const float* d_emb, const float* d_pos) {
@@ -1230,6 +1234,7 @@ int Engine::build_dstep(const Tensor& ckv, const float* d_emb, const float* d_po
   if (!dws) return FPNMT_ERR_CUDA;
   FPNMT_CUDA_OK(cudaMemcpy(dws, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
   p.wstream = dws;
+  p.stream_bytes = ws.size() * 2;
   float* dlp;
   RC(upload_f32(lp, &dlp));
   p.lparams = dlp;
@@ -1253,7 +1258,10 @@ int Engine::build_dstep(const Tensor& ckv, const float* d_emb, const float* d_po
   p.x_stat = (float*)dalloc(xr * DS_CTAS * 2 * 4);
   p.x_cval = (float*)dalloc(xr * DS_CTAS * N * 4);
   p.x_cidx = (int*)dalloc(xr * DS_CTAS * N * 4);
-  if (!p.kcache || !p.vcache || !p.x_att || !p.x_pre || !p.x_part || !p.x_stat || !p.x_cval || !p.x_cidx) return FPNMT_ERR_CUDA;
+  p.gbar = (int*)dalloc((size_t)clusters * sizeof(int));
+  p.rep = (int*)dalloc((size_t)2 * R * sizeof(int));
+  p.ngroups = clusters;
+  if (!p.gbar || !p.rep || !p.kcache || !p.vcache || !p.x_att || !p.x_pre || !p.x_part || !p.x_stat || !p.x_cval || !p.x_cidx) return FPNMT_ERR_CUDA;
   FPNMT_CUDA_OK(cudaMemset(p.x_att, 0, xr * 512 * 2));
   FPNMT_CUDA_OK(cudaMemset(p.x_pre, 0, xr * 512 * 4));
   p.logits_out = logits_;
@@ -1269,6 +1277,8 @@ int Engine::build_dstep(const Tensor& ckv, const float* d_emb, const float* d_po
   }
   p.st = bs_;
   p.mode = 0;
+  p.exp = cfg_.reserved[0];
+  p.timeline = dbg_timeline("dstep");
   RC(dstep_set_attributes());
   // one-step op for the per-op profiler (the product decode is ONE launch of all steps)
   {
@@ -1435,6 +1445,22 @@ int Engine::get_tap_f32(const std::string& name, float* out, size_t cap, size_t*
 }
 
 int Engine::get_tap(const char* name, float* out, size_t cap, size_t* count, cudaStream_t s) {
+#ifdef FPNMT_DBG_STAMPS
+  if (std::string(name) == "dstep_timeline" && use_dstep_ && dsp_.timeline) {   // stamps of the last launch's last step, ns since its start
+    if (count) *count = 192;
+    if (!out) return 0;
+    if (cap < 192) return fail(FPNMT_ERR_INVALID, "get_tap: buffer too small");
+    FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+    long long h[192];
+    FPNMT_CUDA_OK(cudaMemcpy(h, dsp_.timeline, sizeof h, cudaMemcpyDeviceToHost));
+    float f[192] = {0};
+    f[0] = (float)h[0];
+    for (int i = 0; i < (int)h[0] && i < 120; ++i) f[1 + i] = (float)(h[1 + i] - h[1]);
+    for (int i = 150; i < 192; ++i) f[i] = h[i] ? (float)(h[i] - h[1]) : 0.f;     // MMA-warp stamps of one job
+    FPNMT_CUDA_OK(cudaMemcpy(out, f, sizeof f, cudaMemcpyHostToDevice));
+    return 0;
+  }
+#endif
   if (taps_f32_.count(name)) return get_tap_f32(name, out, cap, count, s);
   auto it = taps_.find(name);
   if (it == taps_.end()) return fail(FPNMT_ERR_INVALID, std::string("unknown tap: ") + name);
@@ -1689,11 +1715,18 @@ int Engine::profile(int iters, char* buf, size_t cap) {
     json += ", ";
     RC(profile_program(g0.step, iters, json, "decode_group_step"));
   }
-  char tail[160];
-  snprintf(tail, sizeof tail, ", \"decode_step_t\": %d, \"decode_groups\": %d, \"device_bytes\": %zu}", warm,
-           (int)std::max<size_t>(1, groups_.size()), alloc_bytes_);
+  char tail[240];
+  snprintf(tail, sizeof tail, ", \"decode_step_t\": %d, \"decode_groups\": %d, \"device_bytes\": %zu, \"dstep_groups_per_launch\": %d}", warm,
+           (int)std::max<size_t>(1, groups_.size()), alloc_bytes_, use_dstep_ ? dstep_max_groups(num_sms_) : 0);
   json += tail;
   FPNMT_CUDA_OK(cudaStreamSynchronize(s));
+  if (dbg_buf_ && use_dstep_ && dsp_.timeline) {   // FPNMT_DBG_OP=dstep: phase stamps of the last profiled step (cluster 0, CTA 0)
+    long long h[16 * 9];
+    cudaMemcpy(h, dbg_buf_, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[fpnmt dbg] dstep timeline, %lld stamps (ns since step start):", h[0]);
+    for (int i = 0; i < (int)h[0] && i < 120; ++i) fprintf(stderr, " %lld", h[1 + i] - h[1]);
+    fprintf(stderr, "\n");
+  } else
   if (dbg_buf_) {   // FPNMT_DBG_OP timeline of the last 8 instances (ns relative to each instance's entry)
     long long h[16 * 9];
     cudaMemcpy(h, dbg_buf_, sizeof h, cudaMemcpyDeviceToHost);

@@ -110,7 +110,7 @@ class Engine {
   Tensor enc_out_;                        // (B*16, 512)
   int n_base_ = 16;                       // tokens of the baseline view
   BeamState bs_{};
-  bool use_dstep_ = false;                // cluster-stationary fused decoder (dstep.cuh) instead of the per-operator chain
+  bool use_dstep_ = false;                // group-stationary fused decoder (dstep.cuh) instead of the per-operator chain
   DstepParams dsp_{};
   int prof_t_ = 0;                        // step index used by the single-step op of the fused decoder in profile()
   struct F32Tap { const float* p; size_t count; };

@@ -43,10 +43,10 @@ class Engine:
                  score_mode: str = "log", start_id: int = cfg.START_ID, end_id: int = cfg.END_ID,
                  true_beam: bool = False, use_graphs: bool = True, device: int = 0, opts: Sequence[str] = (),
                  cache_mode: str = "ancestry", decode_path: str = "auto", length_penalty: float = 0.0,
-                 finished_beams: bool = False, dec_groups: int = 0):
+                 finished_beams: bool = False, dec_groups: int = 0, _exp: int = 0):
         """opts: names from _lib.OPT_BITS (e.g. "no_xattn") - each turns one fused kernel back into its unfused equivalent;
-        cache_mode "ancestry" | "physical"; decode_path "auto" (fused cluster-stationary decoder when the configuration
-        allows) | "chain" (per-operator kernels); length_penalty / finished_beams: flagged extensions, 0 = reference."""
+        cache_mode "ancestry" | "physical"; decode_path "auto" (today: the per-operator chain) | "chain" | "fused" (one
+        dstep_kernel launch runs every layer, the vocabulary projection and the beam tail of all steps); length_penalty / finished_beams: flagged extensions, 0 = reference."""
         if not torch.cuda.is_available():
             raise RuntimeError("fpnmt.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -69,6 +69,7 @@ class Engine:
             c.kernel_opts |= _lib.OPT_BITS[o]
         c.cache_mode, c.decode_path = _lib.CACHE_IDS[cache_mode], _lib.DECODE_IDS[decode_path]
         c.length_penalty, c.finished_beams, c.dec_groups = float(length_penalty), int(finished_beams), int(dec_groups)
+        c.reserved[0] = int(_exp)          # developer A/B switches of the fused decoder (dstep.cuh), 0 in product use
         self._h = C.c_void_p()
         torch.cuda.init()
         with torch.cuda.device(self.device):

@@ -54,8 +54,10 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
        FPNMT_OPT_DSTEP_TAPS = 128    /* fused decoder: also keep every layer's LayerNorm outputs (fpnmt_get_tap "decL_outK") */ };
 enum { FPNMT_CACHE_ANCESTRY = 0,     /* KV cache never moves; an ancestry table maps (beam, position) -> physical row    */
        FPNMT_CACHE_PHYSICAL = 1 };   /* KV cache rows are gathered by beam parent after every step (bandwidth kernel)    */
-enum { FPNMT_DECODE_AUTO = 0,        /* cluster-stationary fused decoder (dstep_kernel) whenever the configuration allows */
-       FPNMT_DECODE_CHAIN = 1 };     /* per-operator kernel chain (tgemm / attention / xattn / beam kernels)              */
+enum { FPNMT_DECODE_AUTO = 0,        /* the faster path for the configuration: today the per-operator chain                */
+       FPNMT_DECODE_CHAIN = 1,       /* per-operator kernel chain (tgemm / attention / xattn / beam kernels), 38 per step   */
+       FPNMT_DECODE_FUSED = 2 };     /* group-stationary fused decoder (dstep_kernel): ONE launch runs every layer, the
+                                        vocabulary projection and the beam tail of all steps (bf16, log scores, beam <= 16) */
 
 typedef struct fpnmt_config {
   int32_t backbone;      /* FPNMT_BACKBONE_* — models/mobilenet.py:43, models/resnet.py:78, models/densenet.py:73 */

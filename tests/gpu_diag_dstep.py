@@ -24,7 +24,7 @@ def main():
     ids_ref, len_ref = O.predict_batch_cached(mem, Wv, T, N, 2, 3, num_layers=L, early_stop=False)
     res = {}
     for name, kw in (("chain_x3", dict(precision="bf16x3", decode_path="chain")), ("chain", dict(precision="bf16", decode_path="chain")),
-                     ("fused", dict(precision="bf16", opts=("dstep_taps",)))):
+                     ("fused", dict(precision="bf16", decode_path="fused", opts=("dstep_taps",)))):
         eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, use_graphs=False, **kw)
         for tt in (1, 2, T):
             lg = eng.decode_logits(mem.cuda(), gtok[:, :tt].int().cuda()).cpu()
