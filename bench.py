@@ -388,6 +388,36 @@ def run_own(args, wl):
                        "note": "same workload in the fp32-class mode whose parity bound is the north star's (log-probs 2e-3, "
                                ">= 99 % identical sequences: tests/test_gpu_captions.py); the headline `value` is the bf16 mode"}
         eng3.close()
+    # ---- KV-cache reorder by beam parent as a PHYSICAL move (north-star item 3): same workload with cache_mode="physical";
+    # the reorder kernel's achieved HBM bandwidth comes from the per-op profile (CUDA events, algorithmic bytes = 2 x live cache)
+    kv_physical = None
+    if world == 1 and args.precision == "bf16" and not args.no_parity_mode:
+        wp = init_weights(wl["backbone"], vocab=V, seed=0)
+        engp = Engine(wp, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log",
+                      use_graphs=not args.no_graphs, device=local, cache_mode="physical", decode_path="chain")
+        del wp
+        for i in range(3):
+            ids_p, _ = engp.generate(dev_imgs[i % 2], early_stop=False, to_host=False)
+        torch.cuda.synchronize()
+        kp = max(2, min(args.steps, 4))
+        e0.record(stream)
+        for i in range(kp):
+            ids_p, _ = engp.generate(dev_imgs[i % 2], early_stop=False, to_host=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        msp = e0.elapsed_time(e1) / kp
+        ids_p, _ = engp.generate(dev_imgs[(args.steps - 1) % 2], early_stop=False, to_host=False)   # same batch as ids_check
+        profp = engp.profile(iters=args.profile_iters)
+        ko = [o for o in profp["decode_step"] if o["kind"] == "kvreorder"]
+        gbs = ko[0]["bytes"] / (ko[0]["us"] * 1e-6) / 1e9 if ko else None
+        kv_physical = {"value": B / (msp * 1e-3), "unit": "images/s", "ms_per_step": msp, "steps": kp,
+                       "kernel": "k_kv_reorder (all layers, K and V, one launch per decode step)",
+                       "reorder_us_at_t": ko[0]["us"] if ko else None, "t": profp.get("decode_step_t"),
+                       "algorithmic_bytes": ko[0]["bytes"] if ko else None, "achieved_gbs": gbs,
+                       "frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if gbs else None,
+                       "ids_equal_ancestry_mode": bool(torch.equal(ids_p.cpu(), ids_check.cpu()[:B])) if world == 1 else None,
+                       "note": "the default cache mode (ancestry table) moves 4 bytes per (beam, position) instead"}
+        engp.close()
     cb = None
     if world == 1 and not args.no_cpu:
         cb = cpu_reference_sample(wl, 3, 1)
@@ -406,7 +436,7 @@ def run_own(args, wl):
                     "api": "Engine.generate_stream (fpnmt_stage_images + fpnmt_generate_staged; double-buffered input)",
                     "unpipelined_value": total_images / (ms_e2e_sync * 1e-3)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
-            "parity_mode": parity_mode,
+            "parity_mode": parity_mode, "kv_cache_physical": kv_physical,
             "model_tflops": flop_total / (ms * 1e-3) / 1e12,
             "ids_checksum": int(ids_check.to(torch.int64).sum().item())}
     print(json.dumps(line), flush=True)

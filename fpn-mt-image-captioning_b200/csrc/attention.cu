@@ -514,7 +514,7 @@ constexpr int DEC_WARPS = 4;
 // one warp per (row, head).  Position t = *step is the new token: its K/V come from `qkv` and are appended to the
 // cache at [row][t]; positions t' < t are read from cache row anc[row][t'] (the beam's ancestor at that time).
 template <bool SPLIT>
-__global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_attention(Act qkv, Act kc, Act vc,
+__global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_attention(Act qkv, Act kc0, Act vc0, Act kc1, Act vc1,
                                                                        const int* __restrict__ anc_base, size_t anc_stride,
                                                                        const int* __restrict__ step, int rows, int T,
                                                                        int heads, Act out) {
@@ -539,6 +539,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
     a_o[c] = pos < T ? __ldg(anc_o + pos) : 0;
   }
   const int t = *step;
+  const bool second = kc1.p != nullptr && (t & 1);      // physical cache mode: odd steps live in the second buffer pair
+  const Act kc = second ? kc1 : kc0, vc = second ? vc1 : vc0;
   const int* anc = (t & 1) ? anc_o : anc_e;
   const int a0 = (t & 1) ? a_o[0] : a_e[0], a1 = (t & 1) ? a_o[1] : a_e[1];
   const float2 qv = ld_pair(qkv, row, h * DH, lane);
@@ -578,15 +580,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
     st_act8(out, (size_t)row, h * DH + lane * 8, o);
   }
 }
-int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, size_t anc_stride, const int* step, int rows,
-                              int T, int heads, Act out, cudaStream_t s) {
+int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act vcache2, const int* anc, size_t anc_stride,
+                              const int* step, int rows, int T, int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
   if (kcache.lo)
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                           qkv, kcache, vcache, anc, anc_stride, step, rows, T, heads, out));
+                           qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
   else
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
-                           qkv, kcache, vcache, anc, anc_stride, step, rows, T, heads, out));
+                           qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
   return 0;
 }
 

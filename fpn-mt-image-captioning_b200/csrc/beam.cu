@@ -5,8 +5,8 @@
 //                 phase 2 (last block of each image): merge N x N candidates (ties -> lower flat index n*V+v), emit
 //                 parent/token/score, reorder token sequences and the KV-cache ancestry table by parent, handle <end>
 //                 on the top beam, write the next step's embedding+position rows, advance the device step counter.
-//   k_kv_gather             : physical KV-cache reorder by parent (the bandwidth-bound alternative to the
-//                             ancestry table; used by the "physical" cache mode).
+//   k_kv_reorder            : physical KV-cache reorder by parent, all layers in one launch (the bandwidth-bound
+//                             alternative to the ancestry table; fpnmt_config.cache_mode = FPNMT_CACHE_PHYSICAL).
 #include "kernels.cuh"
 
 namespace fpnmt {
@@ -34,6 +34,7 @@ __global__ void k_beam_init(BeamState st, int true_beam) {
     float s0 = st.prob_mode ? 1.f : 0.f;
     if (true_beam && n > 0) s0 = st.prob_mode ? 0.f : -INFINITY;
     st.score[0][i] = s0;
+    if (st.finished_mode) st.fin_len[0][i] = 0;
     st.seq[0][(size_t)i * (st.T + 1)] = st.start_id;
     st.last_tok[i] = st.start_id;
   }
@@ -93,6 +94,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   const int t = *st.step;
   const float score = st.score[t & 1][row];
   const float* x = logits + (size_t)row * ld;
+  // finished-beam extension: a frozen beam's only candidate is itself (token <end>, score unchanged)
+  const bool row_frozen = st.finished_mode && st.fin_len[t & 1][row] > 0;
+  if (row_frozen) {
+    if (tid < N) {
+      st.cand_val[(size_t)row * N + tid] = tid == 0 ? score : -INFINITY;
+      st.cand_idx[(size_t)row * N + tid] = tid == 0 ? st.end_id : 0x7fffffff;
+    }
+  } else {
   const int nv4 = (V + 4 * THREADS - 1) / (4 * THREADS);  // float4 slots per thread; slot i of thread tid = elements
   float* s_row = reinterpret_cast<float*>(s_row4);        //   (i*THREADS + tid)*4 .. +3 (conflict-free, coalesced)
 
@@ -308,6 +317,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       }
     }
   }
+  }   // !row_frozen
   __syncthreads();
   if (row == 0) BDBG(5);
   if (tid == 0) {
@@ -333,25 +343,37 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     s_token[tid] = 0;
   }
   if (tid == 0) st.img_count[b] = 0;                        // re-armed for the next step
+  float* s_key = s_fv + 2048;                               // [N*N] ranking keys (== values unless the extension is on)
   for (int c = tid; c < NN; c += THREADS) {
     const int tok = __ldcg(st.cand_idx + (size_t)rows0 * N + c);
     const bool ok = tok != 0x7fffffff;
-    s_fv[c] = ok ? __ldcg(st.cand_val + (size_t)rows0 * N + c) : -INFINITY;
+    const float val = ok ? __ldcg(st.cand_val + (size_t)rows0 * N + c) : -INFINITY;
+    s_fv[c] = val;
     s_ff[c] = ok ? (c / N) * V + tok : 0x7fffffff;          // flat index over the N x V candidates
+    float key = val;
+    if (st.finished_mode && ok) {                           // length-normalised score of the candidate
+      const int fl = st.fin_len[cur][rows0 + c / N];
+      key = val / st.lp[fl > 0 ? fl : t + 1];
+    }
+    s_key[c] = key;
   }
   __syncthreads();
   BDBG(8);
   for (int c = tid; c < NN; c += THREADS) {
     const int f = s_ff[c];
     if (f == 0x7fffffff) continue;
-    const float v = s_fv[c];
+    const float v = s_fv[c], key = s_key[c];
     int rank = 0;
-    for (int j = 0; j < NN; ++j) rank += better(s_fv[j], s_ff[j], v, f) ? 1 : 0;
+    for (int j = 0; j < NN; ++j) rank += better(s_key[j], s_ff[j], key, f) ? 1 : 0;
     if (rank < N) {                                         // new beam `rank` (scores sorted, ties -> lower flat index)
       const int par = f / V;                                // pipeline.py:130
       const int tok = f - par * V;                          // pipeline.py:131
       s_parent[rank] = par;
       s_token[rank] = tok;
+      if (st.finished_mode) {
+        const int fl = st.fin_len[cur][rows0 + par];
+        st.fin_len[nxt][rows0 + rank] = fl > 0 ? fl : (tok == st.end_id ? t + 1 : 0);
+      }
       st.score[nxt][rows0 + rank] = v;
       st.last_tok[rows0 + rank] = tok;
       if (st.parent_out) st.parent_out[(size_t)t * st.Btot * N + rows0 + rank] = par;
@@ -366,13 +388,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
     const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
     int* dseq = st.seq[nxt] + (size_t)(rows0 + n) * (T + 1);
     for (int j = lane; j <= t; j += 32) dseq[j] = sseq[j];            // pipeline.py:134-137
-    const int* sanc = st.anc[cur] + (size_t)(rows0 + par) * T;
-    int* danc = st.anc[nxt] + (size_t)(rows0 + n) * T;
-    for (int j = lane; j < t; j += 32) danc[j] = sanc[j];
-    if (lane == 0) {
-      dseq[t + 1] = tok;
-      danc[t] = rows0 + par;
+    if (!st.physical) {                                               // ancestry cache mode: move the indirection, not the cache
+      const int* sanc = st.anc[cur] + (size_t)(rows0 + par) * T;
+      int* danc = st.anc[nxt] + (size_t)(rows0 + n) * T;
+      for (int j = lane; j < t; j += 32) danc[j] = sanc[j];
+      if (lane == 0) danc[t] = rows0 + par;
     }
+    if (lane == 0) dseq[t + 1] = tok;
   }
   BDBG(10);
   // next step's decoder input: x[row] = embedding[token] + pos[t + 1]   (transformer.py:326-329)
@@ -393,9 +415,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   // top beam is rank 0 (scores are sorted; tf.argmax returns the first maximum) — pipeline.py:143-148
   if (warp == 0) {
     const int top_tok = s_token[0];
+    // extension: the image stops when its best beam is a frozen one; its caption ends before the <end> it froze on
+    const int top_fin = st.finished_mode ? st.fin_len[nxt][rows0] : 0;
     if (!st.done[b] && (top_tok == st.end_id || t == T - 1)) {
       const int* res = st.seq[nxt] + (size_t)rows0 * (T + 1);
-      const int len = (top_tok == st.end_id) ? t : t + 1;             // strip <start> and a trailing <end>
+      const int len = top_fin > 0 ? top_fin - 1 : (top_tok == st.end_id) ? t : t + 1;   // strip <start> and a trailing <end>
       for (int j = lane; j < len; j += 32) st.out_ids[(size_t)b * T + j] = res[1 + j];
       __syncwarp();
       if (lane == 0) {
@@ -429,7 +453,7 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
   const int threads = st.V <= 16384 ? 256 : 512;
   const int nv4 = (st.V + 4 * threads - 1) / (4 * threads);
   size_t smem = (size_t)nv4 * threads * 16;
-  if (smem < 8192) smem = 8192;                             // phase 2 keeps the N x N merge list there
+  if (smem < 12288) smem = 12288;                           // phase 2 keeps the N x N merge lists (values, flat ids, keys) there
   if (nv4 > 32 || smem > 200 * 1024) {
     set_last_error("beam_step: vocabulary too large (max 65536)");
     return 1;
@@ -441,25 +465,38 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
   return 0;
 }
 
-// dst[row][0..step][:] = src[src_row[row]][0..step][:]   (16-byte vectors; grid-stride)
-__global__ void k_kv_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ src_row,
-                            int rows, int T, int row_vec, const int* __restrict__ step) {
+// Physical KV-cache reorder (see kernels.cuh).  grid (rows, ncaches): one block streams the live span of one cache row -
+// (tt + 1) * row_bytes contiguous bytes - from its parent's row of the source buffer to its own row of the other buffer with
+// 16-byte loads / stores, 4 in flight per thread.  Bandwidth kernel: 2 x live bytes of HBM traffic, nothing else.
+__global__ void __launch_bounds__(256) k_kv_reorder(const bf16* const* __restrict__ bufs, int ncaches, const int* __restrict__ parent,
+                                                    int rows_total, int N, int T, int row_bytes, const int* __restrict__ step) {
   pdl_launch();
   pdl_wait();
-  const int t = *step;   // positions 0..t are live
-  const size_t per_row = (size_t)(t + 1) * row_vec;
-  const size_t total = (size_t)rows * per_row;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / per_row);
-    const size_t off = i % per_row;
-    dst[(size_t)r * T * row_vec + off] = src[(size_t)src_row[r] * T * row_vec + off];
+  const int tt = *step - 1;                        // the decode step that has just been closed by the beam kernel
+  if (tt < 0) return;
+  const int r = blockIdx.x, c = blockIdx.y;
+  const int src_row = (r / N) * N + parent[(size_t)tt * rows_total + r];
+  const size_t row_stride = (size_t)T * row_bytes;
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(bufs[(tt & 1) * ncaches + c]) + src_row * row_stride);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(const_cast<bf16*>(bufs[((tt + 1) & 1) * ncaches + c])) + r * row_stride);
+  const int n = (tt + 1) * (row_bytes / 16);
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < n; i += 4 * 256) {
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + 256), d = __ldcs(src + i + 512), e = __ldcs(src + i + 768);
+    __stcs(dst + i, a);
+    __stcs(dst + i + 256, b);
+    __stcs(dst + i + 512, d);
+    __stcs(dst + i + 768, e);
   }
+  for (; i < n; i += 256) __stcs(dst + i, __ldcs(src + i));
 }
-int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
-                     cudaStream_t s) {
-  const int row_vec = row_elems / 8;
-  FPNMT_CUDA_OK(launch_k(k_kv_gather, dim3(148 * 8), dim3(256), 0, s, reinterpret_cast<const uint4*>(src),
-                         reinterpret_cast<uint4*>(dst), src_row, rows, T, row_vec, step));
+int launch_kv_reorder(const bf16* const* bufs, int ncaches, const int* parent, int rows, int rows_total, int N, int T, int row_bytes,
+                      const int* step, cudaStream_t s) {
+  if (row_bytes % 16) {
+    set_last_error("kv_reorder: cache rows must be a multiple of 16 bytes");
+    return 1;
+  }
+  FPNMT_CUDA_OK(launch_k(k_kv_reorder, dim3(rows, ncaches), dim3(256), 0, s, bufs, ncaches, parent, rows_total, N, T, row_bytes, step));
   return 0;
 }
 

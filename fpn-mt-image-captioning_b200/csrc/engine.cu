@@ -839,6 +839,8 @@ int Engine::build_mt_encoder(Program& p) {
   return 0;
 }
 
+__global__ void k_anc_identity(int* anc, int rows, int T);
+
 // KV-cached decoder step programs (transformer.py:224-243, 321-341, 372) + decode tail (pipeline.py:115-148)
 int Engine::build_decoder() {
   const int B = cfg_.batch, N = cfg_.beam, D = cfg_.d_model, L = cfg_.num_layers, H = cfg_.num_heads, FF = cfg_.dff;
@@ -862,6 +864,21 @@ int Engine::build_decoder() {
   bs_.n_done = (int*)dalloc(16);
   bs_.img_count = (int*)dalloc((size_t)B * 4);
   FPNMT_CUDA_OK(cudaMemset(bs_.img_count, 0, (size_t)B * 4));
+  bs_.finished_mode = cfg_.finished_beams ? 1 : 0;
+  if (bs_.finished_mode) {   // extension: frozen finished beams + length penalty lp[len] = ((5 + len) / 6)^alpha
+    bs_.fin_len[0] = (int*)dalloc((size_t)R * 4);
+    bs_.fin_len[1] = (int*)dalloc((size_t)R * 4);
+    std::vector<float> lp(T + 2);
+    for (int i = 0; i < T + 2; ++i) lp[i] = powf((5.f + (float)i) / 6.f, cfg_.length_penalty);
+    float* dlp;
+    RC(upload_f32(lp, &dlp));
+    bs_.lp = dlp;
+    if (!bs_.fin_len[0] || !bs_.fin_len[1]) return FPNMT_ERR_CUDA;
+    FPNMT_CUDA_OK(cudaMemset(bs_.fin_len[0], 0, (size_t)R * 4));
+    FPNMT_CUDA_OK(cudaMemset(bs_.fin_len[1], 0, (size_t)R * 4));
+  } else if (cfg_.length_penalty != 0.f) {
+    return fail(FPNMT_ERR_INVALID, "length_penalty needs finished_beams = 1 (it only orders beams of different lengths)");
+  }
   bs_.out_ids = (int*)dalloc((size_t)B * T * 4);
   bs_.out_len = (int*)dalloc((size_t)B * 4);
   bs_.cand_val = (float*)dalloc((size_t)R * N * 4);
@@ -955,10 +972,17 @@ int Engine::build_decoder() {
     }
 
     // ---- per-layer weights and full-batch buffers (allocated once; chains below work on row slices of them)
+    const bool physical = cfg_.cache_mode == FPNMT_CACHE_PHYSICAL;
+    if (physical && cfg_.dec_groups > 1) return fail(FPNMT_ERR_INVALID, "cache_mode PHYSICAL does not combine with dec_groups");
+    bs_.physical = physical ? 1 : 0;
+    if (physical) {   // the ancestry tables stay the identity in this mode
+      k_anc_identity<<<148, 256>>>(anc, R, T);
+      FPNMT_CUDA_OK(cudaGetLastError());
+    }
     struct LayerW {
       GemmW gqkv, go1, gq2, go2, g1, g2;
       float* lnp[6];
-      Tensor qkv, att, out1, q2, att2, out2, hdn, out3, kc, vc;
+      Tensor qkv, att, out1, q2, att2, out2, hdn, out3, kc, vc, kc2, vc2;
       float* y;
     };
     std::vector<LayerW> lw(L);
@@ -976,6 +1000,11 @@ int Engine::build_decoder() {
       w.qkv = rows_act(R, 3 * D); w.att = rows_act(R, D); w.out1 = rows_act(R, D); w.q2 = rows_act(R, D);
       w.att2 = rows_act(R, D); w.out2 = rows_act(R, D); w.hdn = rows_act(R, FF); w.out3 = rows_act(R, D);
       w.kc = rows_act(R * T, D); w.vc = rows_act(R * T, D);
+      if (physical) {   // second buffer pair: every step's reorder gathers from one pair into the other
+        w.kc2 = rows_act(R * T, D);
+        w.vc2 = rows_act(R * T, D);
+        if (!w.kc2.a.p || !w.vc2.a.p) return FPNMT_ERR_CUDA;
+      }
       w.y = (float*)dalloc((size_t)R * D * 4);
     }
     GemmW gf;
@@ -1011,6 +1040,7 @@ int Engine::build_decoder() {
                q2 = row_view(w.q2, r0, Rg), att2 = row_view(w.att2, r0, Rg), out2 = row_view(w.out2, r0, Rg),
                hdn = row_view(w.hdn, r0, Rg), out3 = row_view(w.out3, r0, Rg);
         Tensor kc = row_view(w.kc, (size_t)r0 * T, Rg * T), vc = row_view(w.vc, (size_t)r0 * T, Rg * T);
+        Tensor kc2 = physical ? row_view(w.kc2, (size_t)r0 * T, Rg * T) : Tensor(), vc2 = physical ? row_view(w.vc2, (size_t)r0 * T, Rg * T) : Tensor();
         float* y = w.y + (size_t)r0 * D;
         // Dense layers of the step: skinny-row tgemm (weights prefetched before the grid dependency, LayerNorm fused
         // into the epilogue by a 4-CTA cluster) or, with FPNMT_TGEMM=0, the generic igemm + separate LayerNorm kernels.
@@ -1028,12 +1058,16 @@ int Engine::build_decoder() {
         };
         RC(dense(ln + "_qkv", x, w.gqkv, ACT_NONE, qkv));
         {
-          Act qa = qkv.a, ka = kc.a, va = vc.a, oa = att.a;
+          Act qa = qkv.a, ka = kc.a, va = vc.a, oa = att.a, ka2 = kc2.a, va2 = vc2.a;
           const int* ancp = anc + (size_t)r0 * T;
           const size_t anc_stride = (size_t)R * T;
           const int* step = bs.step;
           Op o = ew_op(ln + "_self_attn" + sfx,
-                       [=](cudaStream_t s) { return launch_dec_self_attention(qa, ka, va, ancp, anc_stride, step, Rg, T, H, oa, s); },
+                       [=](cudaStream_t s) {
+                         // teacher forcing (decode_logits) has no beam step and therefore no reorder: it stays in the first buffer pair
+                         const Act none{nullptr, 0, 0, 0};
+                         return launch_dec_self_attention(qa, ka, va, forced_mode_ ? none : ka2, forced_mode_ ? none : va2, ancp, anc_stride, step, Rg, T, H, oa, s);
+                       },
                        (double)Rg * (T / 2) * 2 * D * 2, "attention");
           step_prog.push_back(std::move(o));
         }
@@ -1080,6 +1114,26 @@ int Engine::build_decoder() {
       {
         Op o = ew_op("beam_step" + sfx, [=](cudaStream_t s) { return launch_beam_step(bs, lg, V, em, s); },
                      (double)Rg * V * 4 + (double)Rg * (T + 1) * 8, "beam");
+        o.idempotent = false;
+        step_prog.push_back(std::move(o));
+      }
+      if (physical) {
+        // KV-cache reorder by beam parent, all layers and K / V in one bandwidth-bound launch (north-star item 3)
+        std::vector<const bf16*> hp(2 * 2 * L);
+        for (int l = 0; l < L; ++l) {
+          hp[2 * l] = lw[l].kc.a.p;
+          hp[2 * l + 1] = lw[l].vc.a.p;
+          hp[2 * L + 2 * l] = lw[l].kc2.a.p;
+          hp[2 * L + 2 * l + 1] = lw[l].vc2.a.p;
+        }
+        const bf16** dp = (const bf16**)dalloc(hp.size() * sizeof(bf16*));
+        if (!dp) return FPNMT_ERR_CUDA;
+        FPNMT_CUDA_OK(cudaMemcpy(dp, hp.data(), hp.size() * sizeof(bf16*), cudaMemcpyHostToDevice));
+        const int row_bytes = lw[0].kc.a.ld * 2;
+        const int* par = bs.parent_out;
+        const int* step = bs.step;
+        Op o = ew_op("kv_reorder_physical", [=](cudaStream_t s) { return launch_kv_reorder(dp, 2 * L, par, R, R, N, T, row_bytes, step, s); },
+                     2.0 * 2 * L * (double)R * (T / 2 + 1) * row_bytes, "kvreorder");
         o.idempotent = false;
         step_prog.push_back(std::move(o));
       }
@@ -1506,6 +1560,8 @@ int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, flo
   RC(run_program(dec_init_prog_, s));
   k_forced_init<<<(R + 255) / 256, 256, 0, s>>>(bs_, tokens, t);
   FPNMT_CUDA_OK(cudaGetLastError());
+  forced_mode_ = true;
+  struct Reset { bool& f; ~Reset() { f = false; } } reset{forced_mode_};
   for (int i = 0; i < t; ++i) {
     if (use_dstep_) {   // fused decoder, teacher-forcing mode: one step, fp32 logits of every row written out
       DstepParams q = dsp_;

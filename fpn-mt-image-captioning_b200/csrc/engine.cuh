@@ -112,6 +112,7 @@ class Engine {
   BeamState bs_{};
   bool use_dstep_ = false;                // group-stationary fused decoder (dstep.cuh) instead of the per-operator chain
   DstepParams dsp_{};
+  bool forced_mode_ = false;              // decode_logits is running (physical cache mode: no buffer alternation)
   int prof_t_ = 0;                        // step index used by the single-step op of the fused decoder in profile()
   struct F32Tap { const float* p; size_t count; };
   std::map<std::string, F32Tap> taps_f32_;

@@ -56,8 +56,9 @@ int launch_enc_attention_views(Act q, const Act* kvs, const int* tks, const int*
 // Decoder self-attention, one new position per row, KV cache with beam-ancestry indirection.
 // qkv: [rows][3*d] (q|k|v) of the new position; caches [rows][T][d]; anc [2][..][T] physical row per position, the two
 // step parities `anc_stride` ints apart (rows may be a slice of a larger batch: anc_stride = total rows * T).
-int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, const int* anc, size_t anc_stride, const int* step, int rows,
-                              int T, int heads, Act out, cudaStream_t s);
+// kcache2 / vcache2 (p != nullptr): physical cache mode - odd steps read and append to the second buffer pair.
+int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act vcache2, const int* anc, size_t anc_stride,
+                              const int* step, int rows, int T, int heads, Act out, cudaStream_t s);
 // Decoder cross-attention over the 16 memory tokens of the row's image.
 int launch_dec_cross_attention(Act q, Act kv, int k_col, int v_col, int rows, int beam, int Tk, int heads, Act out,
                                cudaStream_t s);
@@ -84,6 +85,14 @@ struct BeamState {
   int* parent_out;           // optional [T][B*N] parents chosen per step (debug / parity), may be null
   int* token_out;            // optional [T][B*N]
   long long* dbg;            // optional globaltimer stamps of image 0 (FPNMT_DBG_OP=beam_step), else nullptr
+  // EXTENSION (fpnmt_config.finished_beams / length_penalty; 0 / 0 = the reference, pipeline.py:143-148): a beam that has
+  // emitted <end> is frozen - it contributes ONE candidate (itself, score unchanged) to the next ranking instead of V - and
+  // candidates are ranked by score / lp[length] with lp[len] = ((5 + len) / 6)^alpha (host table, lp[.] = 1 for alpha = 0).
+  int finished_mode;
+  int* fin_len[2];           // [B*N] per step parity: 0 = live beam, else the length (tokens incl. <end>) at which it finished
+  const float* lp;           // [T + 1] length-penalty table
+  int physical;              // 1: "physical" KV-cache mode - the ancestry tables stay the identity (never written here) and
+                             // launch_kv_reorder moves the cache rows by beam parent after every step
 };
 // true_beam = 0 reproduces the reference (all beams start identical, pipeline.py:101-102); 1 starts beams 1..N-1 dead
 int launch_beam_init(const BeamState& st, int true_beam, cudaStream_t s);
@@ -98,8 +107,12 @@ struct BeamEmbed {
 // (last block of each image) merge N x N candidates, emit parents/tokens/scores, reorder sequences + ancestry, handle
 // <end>, write the next decoder input, advance the step counter.  Buffers are double-buffered on (step & 1).
 int launch_beam_step(const BeamState& st, const float* logits, int ld, const BeamEmbed& em, cudaStream_t s);
-// Physical KV reorder variant: dst[row] = src[parent-mapped row] for positions <= step (bandwidth kernel).
-int launch_kv_gather(const bf16* src, bf16* dst, const int* src_row, int rows, int T, int row_elems, const int* step,
-                     cudaStream_t s);
+// Physical KV-cache reorder by beam parent (pipeline.py:134-137 applied to the cache instead of an indirection table), ALL
+// layers and both of K / V in one launch: after decode step tt = *step - 1, for every row r of the batch
+//   buf[(tt + 1) & 1][c][r][0..tt] = buf[tt & 1][c][(r / N) * N + parent[tt][r]][0..tt]      c = 0 .. ncaches - 1
+// where a cache row's live positions are one contiguous span of (tt + 1) * row_bytes bytes.  `bufs` is a device array of
+// 2 * ncaches base pointers ([parity][cache]); parent = BeamState::parent_out ([T][rows_total], local beam index).
+int launch_kv_reorder(const bf16* const* bufs, int ncaches, const int* parent, int rows, int rows_total, int N, int T, int row_bytes,
+                      const int* step, cudaStream_t s);
 
 }  // namespace fpnmt

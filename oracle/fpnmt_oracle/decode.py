@@ -49,6 +49,26 @@ def beam_step(logits: np.ndarray, beam_score: np.ndarray, mode: str = "prob"):
     return parent, token, vals.astype(np.float32)
 
 
+def _beam_step_finished(logits: np.ndarray, beam_score: np.ndarray, fin_len: np.ndarray, lp: np.ndarray, t: int, end_token: int):
+    """One step of the finished-beam / length-penalty extension for one image (see predict_batch_cached)."""
+    n, v = logits.shape
+    raw = (torch.log_softmax(torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32)), dim=-1).numpy()
+           + beam_score.astype(np.float32)[:, None])
+    key = np.full((n, v), -np.inf, np.float32)
+    for b in range(n):
+        if fin_len[b] > 0:
+            raw[b, :] = -np.inf
+            raw[b, end_token] = beam_score[b]                              # the frozen beam itself
+            key[b, end_token] = np.float32(beam_score[b]) / lp[fin_len[b]]
+        else:
+            key[b] = raw[b] / lp[t + 1]
+    _, idx = top_k_stable(key.reshape(-1), n)
+    parent = idx // v
+    token = idx - parent * v
+    new_fin = np.where(fin_len[parent] > 0, fin_len[parent], np.where(token == end_token, t + 1, 0))
+    return parent, token, raw.reshape(-1)[idx].astype(np.float32), new_fin
+
+
 def strip_result(seq: np.ndarray, end_token: int) -> np.ndarray:
     """pipeline.py:147-154: drop <start>, and the trailing <end> if present."""
     return seq[1:-1] if seq[-1] == end_token else seq[1:]
@@ -120,7 +140,8 @@ def _dec_step_cached(w: W, tok: torch.Tensor, pos_row: torch.Tensor, caches: Lis
 
 def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam: int, start_token: int,
                          end_token: int, num_layers: int = 6, num_heads: int = 8, early_stop: bool = True,
-                         trace: Optional[dict] = None, true_beam: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+                         trace: Optional[dict] = None, true_beam: bool = False, finished_beams: bool = False,
+                         length_penalty: float = 0.0) -> Tuple[np.ndarray, np.ndarray]:
     """Batched KV-cached beam decode with log-domain scores.
 
     enc_output (B,16,d).  Returns (ids (B,max_seq_len) int32 padded with 0, lengths (B,) int32), each row being
@@ -129,7 +150,16 @@ def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam:
     true_beam=True is the flagged EXTENSION (not reference behaviour): only beam 0 is alive at t = 0
     (log-score 0, the others -inf), so the N beams diverge instead of staying N copies of the greedy path
     (pipeline.py:101-102 starts all N identical).
+    finished_beams=True / length_penalty=alpha is the second flagged EXTENSION: a beam that has emitted <end> is frozen (it
+    contributes one candidate - itself, score unchanged - instead of V), candidates are ranked by score / lp(length) with
+    lp(len) = ((5 + len) / 6) ** alpha (length = generated tokens including <end>), and an image stops when its BEST beam is a
+    frozen one.  finished_beams=False, alpha=0 is the reference (pipeline.py:143-148: stop the moment the top beam emits <end>;
+    lower beams that emitted <end> keep decoding).
     """
+    if length_penalty != 0.0 and not finished_beams:
+        raise ValueError("length_penalty only orders beams of different lengths: it needs finished_beams=True")
+    lp = np.array([np.power(np.float32((5.0 + i) / 6.0), np.float32(length_penalty)) for i in range(max_seq_len + 2)], np.float32)
+    fin_len = np.zeros((enc_output.shape[0], beam), np.int64)
     bsz, _, d = enc_output.shape
     rows = bsz * beam
     enc_rows = enc_output.repeat_interleave(beam, dim=0)
@@ -154,7 +184,10 @@ def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam:
         gparent = np.zeros((bsz, beam), np.int64)
         new_seqs = np.zeros((bsz, beam, t + 2), np.int64)
         for b in range(bsz):
-            parent, token, sc = beam_step(logits[b], score[b], "log")
+            if finished_beams:
+                parent, token, sc, fin_len[b] = _beam_step_finished(logits[b], score[b], fin_len[b], lp, t, end_token)
+            else:
+                parent, token, sc = beam_step(logits[b], score[b], "log")
             gparent[b] = b * beam + parent
             new_seqs[b] = np.concatenate([seqs[b][parent], token[:, None]], axis=-1)
             score[b] = sc
@@ -167,7 +200,9 @@ def predict_batch_cached(enc_output: torch.Tensor, w: W, max_seq_len: int, beam:
         for b in range(bsz):
             if done[b]:
                 continue
-            res = seqs[b, int(np.argmax(score[b]))]
+            res = seqs[b, int(np.argmax(score[b]))] if not finished_beams else seqs[b, 0]
+            if finished_beams and fin_len[b, 0] > 0:            # best beam is frozen: its caption ends before its <end>
+                res = res[:fin_len[b, 0] + 1]
             if res[-1] == end_token or t == max_seq_len - 1:
                 r = strip_result(res, end_token)
                 out_ids[b, :len(r)] = r

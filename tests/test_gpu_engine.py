@@ -9,7 +9,10 @@ Tolerances (stated here, checked below):
   BF16 fast mode     : a random-init BatchNorm network amplifies perturbations by ~1.2x per layer (rounding every conv
                        operand/output to bf16 in the ORACLE already moves C5 by 40-50 % on these weights), so a fixed
                        stage bound would be meaningless.  The stated bound is relative to that emulation: per stage,
-                       rel-L2(engine, oracle) <= max(8e-2, 1.6 x rel-L2(oracle with bf16-rounded convolutions, oracle)).
+                       rel-L2(engine, oracle) <= max(5e-2 [head outputs: 9e-2], 1.2 x rel-L2(oracle with bf16-rounded
+                       convolutions, oracle)).  Measured (profiles/r02_a_parity_stage_errors.json): the engine's error is
+                       0.85-1.09 x the emulation's at every tap of the three backbones - it IS the bf16 rounding of this
+                       random BatchNorm network, nothing else - and 2-8 % where the network does not amplify (DenseNet).
                        Decoder (fed with the oracle's memory): log-probs within 0.25 absolute at logit std ~6,
                        per-step arg-max agreement >= 85 %.  Sequence identity is NOT required.
 """
@@ -59,7 +62,7 @@ def setup(request):
     return dict(bb=bb, w=w, Wv=Wv, img=img, taps=taps, mem_ref=mem_ref, taps_emu=taps_emu, mem_emu=mem_emu)
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-3), ("bf16", 8e-2)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-3), ("bf16", 5e-2)])
 def test_encoder_stages(setup, prec, tol):
     from fpnmt.engine import Engine
     s = setup
@@ -71,8 +74,8 @@ def test_encoder_stages(setup, prec, tol):
 
     def check(key, got, ref, ref_emu):
         errs[key] = rel(got.cpu().reshape(ref.shape), ref)
-        base = tol * 1.5 if key.startswith("feat") else tol
-        bound[key] = base if prec == "bf16x3" else max(base, 1.6 * rel(ref_emu, ref))
+        base = tol * (1.5 if prec == "bf16x3" else 1.8) if key.startswith("feat") else tol
+        bound[key] = base if prec == "bf16x3" else max(base, 1.2 * rel(ref_emu, ref))
 
     for nm in ("C3", "C4", "C5", "P3", "P4", "P5", "P6", "P7"):
         check(nm, eng.tap(nm), taps[nm], emu[nm])
