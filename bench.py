@@ -9,7 +9,10 @@ BASELINE.json: ResNet-50-FPN + Multi-Transformer, beam 8, batch 64, 3x512x512 sy
 random-init weights, V=10000, T=64 decode steps, early stop OFF (fixed work).
 
   value  images/s, inputs already resident in HBM, ids left on the device (+ NCCL all-gather of ids for N>1),
+         through the streaming call with `--lanes` batches in flight per GPU (default 2: the encoder of batch i+1 runs
+         under the decode of batch i; every batch is submitted and collected inside the timed region),
          timed with CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  one_shot  the same batches one at a time through Engine.generate (the latency of a batch; ids equal to the streamed ones).
   e2e    images/s through the public streaming call (Engine.generate_stream == fpnmt_stage_images +
          fpnmt_generate_staged, what Pipeline.evaluate uses) with PINNED HOST images and host results: every step's
          H2D copy of its batch and D2H read of ids/lengths are inside the timed region; the copy of batch i+1 is
@@ -209,7 +212,7 @@ def run_own(args, wl):
     B, N, V, T = wl["batch"], wl["beam"], wl["vocab"], wl["max_len"]
     w = init_weights(wl["backbone"], vocab=V, seed=0)
     eng = Engine(w, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision=args.precision,
-                 score_mode="log", use_graphs=not args.no_graphs, device=local)
+                 score_mode="log", use_graphs=not args.no_graphs, device=local, lanes=args.lanes)
     del w
     g = torch.Generator().manual_seed(1234 + rank)
     host_imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).pin_memory() for _ in range(2)]
@@ -217,8 +220,18 @@ def run_own(args, wl):
     stream = torch.cuda.current_stream(dev)
 
     def step_device(i):
+        """One-shot call: one batch, nothing else in flight (the latency figure; `one_shot` in the JSON line)."""
         ids, lens = eng.generate(dev_imgs[i % 2], early_stop=False, to_host=False)
         return fd.allgather_captions(ids, lens, world)
+
+    def run_device(n):
+        """n whole batches, inputs resident in HBM, through the public streaming call: with lanes >= 2 up to `lanes` batches
+        are in flight (fpnmt_submit / fpnmt_collect), so the encoder of batch i+1 runs under the decode of batch i.  Every
+        batch is submitted and collected inside the caller's timed region (pipeline fill and drain included)."""
+        out = None
+        for ids, lens in eng.generate_stream((dev_imgs[i % 2] for i in range(n)), early_stop=False, to_host=False):
+            out = fd.allgather_captions(ids, lens, world)
+        return out
 
     def finish_host(ids, lens):
         if world > 1:
@@ -238,6 +251,7 @@ def run_own(args, wl):
 
     for i in range(max(args.warmup, 3)):
         step_device(i)
+    run_device(max(args.warmup, 3))
     torch.cuda.synchronize()
     if args.ncu_step:        # `ncu --profile-from-start off ... bench.py --ncu-step`: capture exactly ONE whole step
         torch.cuda.cudart().cudaProfilerStart()
@@ -253,8 +267,7 @@ def run_own(args, wl):
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
-        out = step_device(i)
+    out = run_device(args.steps)
     e1.record(stream)
     torch.cuda.synchronize()
     fd.barrier()
@@ -262,6 +275,17 @@ def run_own(args, wl):
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     ids_check = out[0]
+    # ---- one batch at a time (nothing else in flight): the latency of a batch, and the cross-check of the lanes' results
+    k1 = max(2, min(args.steps, 6))
+    fd.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(k1):
+        out1 = step_device(args.steps - k1 + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_one = fd.max_over_ranks(e0.elapsed_time(e1), dev) / k1
+    lanes_equal = bool(torch.equal(out1[0].cpu(), ids_check.cpu()))      # same last batch, one-shot vs streamed through the lanes
     # ---- end-to-end timing (host buffers)
     run_host(2)
     torch.cuda.synchronize()
@@ -287,6 +311,7 @@ def run_own(args, wl):
     value = total_images / (ms * 1e-3)
     e2e_value = total_images / (ms_e2e * 1e-3)
     # ---- roofline of the dominant kernel, measured live with the engine's per-op CUDA-event profiler
+    eng_lanes = eng.lanes
     prof = eng.profile(iters=args.profile_iters)
     if args.profile_out:
         with open(args.profile_out, "w") as f:
@@ -430,11 +455,20 @@ def run_own(args, wl):
                        "max_len": T, "image": "512x512x3 f32 NHWC", "weights": "random init (Keras default distributions)",
                        "l2": "per-step inputs (%.0f MB) and activations (GBs) exceed the 126 MB L2; two input batches alternate"
                              % (B * 512 * 512 * 3 * 4 / 1e6),
-                       "cuda_graphs": not args.no_graphs, "decoder_groups": n_groups, "parallelism": "dp%d (image-sharded, ids all-gather)" % world},
+                       "cuda_graphs": not args.no_graphs, "decoder_groups": n_groups, "lanes": eng_lanes,
+                       "pipelining": ("%d batches in flight per GPU (fpnmt_submit/fpnmt_collect): encoder of batch i+1 under the "
+                                      "decode of batch i; every batch submitted and collected inside the timed region" % eng_lanes)
+                                     if eng_lanes > 1 else "none (one batch at a time)",
+                       "parallelism": "dp%d (image-sharded, ids all-gather)" % world},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 512 * 512 * 3 * 4,
                     "d2h_bytes_per_step": B * T * 4 + B * 4, "ms_per_step": ms_e2e / args.steps,
-                    "api": "Engine.generate_stream (fpnmt_stage_images + fpnmt_generate_staged; double-buffered input)",
+                    "api": ("Engine.generate_stream (fpnmt_submit + fpnmt_collect, %d lanes: pinned-host copy, encoder and decode of "
+                            "different batches overlap)" % eng_lanes) if eng_lanes > 1 else
+                           "Engine.generate_stream (fpnmt_stage_images + fpnmt_generate_staged; double-buffered input)",
                     "unpipelined_value": total_images / (ms_e2e_sync * 1e-3)},
+            "one_shot": {"value": B * world / (ms_one * 1e-3), "unit": "images/s", "ms_per_batch": ms_one, "steps": k1,
+                         "api": "Engine.generate (one batch, nothing else in flight, device-resident inputs)",
+                         "ids_equal_streamed": lanes_equal},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
             "parity_mode": parity_mode, "kv_cache_physical": kv_physical,
             "model_tflops": flop_total / (ms * 1e-3) / 1e12,
@@ -451,6 +485,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="batches in flight per GPU (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 throughput leg (parity_mode key)")
     ap.add_argument("--profile-iters", type=int, default=10)

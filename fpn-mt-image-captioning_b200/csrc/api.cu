@@ -20,7 +20,8 @@ bool pdl_small_enabled() { return g_pdl_mode == 1; }
 using namespace fpnmt;
 
 struct fpnmt_handle {
-  Engine* eng;
+  Engine* eng;                   // lane 0: every single-batch entry point runs here
+  std::vector<Engine*> lanes;    // lanes[0] == eng; fpnmt_submit / fpnmt_collect address the others
 };
 
 extern "C" {
@@ -44,20 +45,31 @@ FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** o
     set_last_error("fpnmt_create: bad device index");
     return FPNMT_ERR_INVALID;
   }
-  Engine* e = new (std::nothrow) Engine(*cfg, device);
-  if (!e) return FPNMT_ERR_INVALID;
-  int rc = e->init();
-  if (rc) {
-    delete e;
-    return rc;
+  if (cfg->lanes < 0 || cfg->lanes > 8) {
+    set_last_error("fpnmt_create: lanes must be 0..8");
+    return FPNMT_ERR_INVALID;
   }
-  *out = new fpnmt_handle{e};
+  const int L = cfg->lanes < 1 ? 1 : cfg->lanes;
+  fpnmt_handle* h = new fpnmt_handle{nullptr, {}};
+  for (int l = 0; l < L; ++l) {
+    Engine* e = new (std::nothrow) Engine(*cfg, device);
+    int rc = e ? e->init() : FPNMT_ERR_INVALID;
+    if (rc) {
+      delete e;
+      for (Engine* p : h->lanes) delete p;
+      delete h;
+      return rc;
+    }
+    h->lanes.push_back(e);
+  }
+  h->eng = h->lanes[0];
+  *out = h;
   return FPNMT_OK;
 }
 
 FPNMT_API int fpnmt_destroy(fpnmt_handle* h) {
   if (!h) return FPNMT_OK;
-  delete h->eng;
+  for (Engine* p : h->lanes) delete p;
   delete h;
   return FPNMT_OK;
 }
@@ -70,11 +82,36 @@ FPNMT_API int fpnmt_destroy(fpnmt_handle* h) {
 
 FPNMT_API int fpnmt_set_weight(fpnmt_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
   CHECK_H(h);
-  return h->eng->set_weight(key, data, shape, ndim);
+  for (Engine* e : h->lanes) {
+    const int rc = e->set_weight(key, data, shape, ndim);
+    if (rc) return rc;
+  }
+  return FPNMT_OK;
 }
 FPNMT_API int fpnmt_finalize_weights(fpnmt_handle* h) {
   CHECK_H(h);
-  return h->eng->finalize();
+  for (Engine* e : h->lanes) {
+    const int rc = e->finalize();
+    if (rc) return rc;
+  }
+  return FPNMT_OK;
+}
+FPNMT_API int fpnmt_lanes(fpnmt_handle* h) { return h ? (int)h->lanes.size() : 0; }
+FPNMT_API int fpnmt_submit(fpnmt_handle* h, int lane, const float* images, int on_host, int early_stop, void* stream) {
+  CHECK_H(h);
+  if (lane < 0 || lane >= (int)h->lanes.size()) {
+    set_last_error("fpnmt_submit: lane out of range (fpnmt_config.lanes)");
+    return FPNMT_ERR_INVALID;
+  }
+  return h->lanes[lane]->submit(images, on_host, early_stop, (cudaStream_t)stream);
+}
+FPNMT_API int fpnmt_collect(fpnmt_handle* h, int lane, int32_t* out_ids, int32_t* out_len, int outputs_on_host, void* stream) {
+  CHECK_H(h);
+  if (lane < 0 || lane >= (int)h->lanes.size()) {
+    set_last_error("fpnmt_collect: lane out of range (fpnmt_config.lanes)");
+    return FPNMT_ERR_INVALID;
+  }
+  return h->lanes[lane]->collect(out_ids, out_len, outputs_on_host, (cudaStream_t)stream);
 }
 FPNMT_API int fpnmt_encode(fpnmt_handle* h, const float* images, int on_host, float* memory_out, void* stream) {
   CHECK_H(h);
@@ -124,7 +161,9 @@ FPNMT_API int fpnmt_profile(fpnmt_handle* h, int iters, char* buf, size_t cap) {
 }
 FPNMT_API int64_t fpnmt_launch_count(fpnmt_handle* h) {
   if (!h || !h->eng) return 0;
-  return h->eng->launches;
+  int64_t n = 0;
+  for (Engine* e : h->lanes) n += e->launches;
+  return n;
 }
 
 // ---- stand-alone convolution operator -----------------------------------------------------------------

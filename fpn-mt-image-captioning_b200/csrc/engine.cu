@@ -55,6 +55,12 @@ Engine::~Engine() {
     if (stage_ready_[i]) cudaEventDestroy(stage_ready_[i]);
     if (stage_free_[i]) cudaEventDestroy(stage_free_[i]);
   }
+  if (lane_stream_) {
+    cudaStreamSynchronize(lane_stream_);
+    cudaStreamDestroy(lane_stream_);
+  }
+  if (lane_in_ev_) cudaEventDestroy(lane_in_ev_);
+  if (lane_out_ev_) cudaEventDestroy(lane_out_ev_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
   for (void* p : allocs_) cudaFree(p);
 }
@@ -1700,6 +1706,58 @@ int Engine::generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int ou
   FPNMT_CUDA_OK(cudaEventRecord(stage_free_[slot], s));
   stage_filled_[slot] = false;
   return decode(out_ids, out_len, out_on_host, early_stop, step_scores, s);
+}
+
+// Lane interface.  submit() enqueues a whole batch on the engine's own stream and returns; collect() hands the result over.
+// Device-resident images are ordered against the caller's stream with an event (they must stay valid until collect); host
+// images are copied into the lane's staging buffer on the lane stream (pinned memory for a truly asynchronous copy; the buffer
+// must stay valid until collect).  A fixed-length decode is enqueued completely at submit; an early-stop decode needs the host
+// to look at the finished-image counter, so submit enqueues the encoder only and collect drives the decode - the encoder of the
+// batch submitted on another lane in between still overlaps it.
+int Engine::submit(const float* images, int on_host, int early_stop, cudaStream_t caller) {
+  if (!finalized_) return fail(FPNMT_ERR_STATE, "submit before finalize_weights");
+  if (lane_state_ != 0) return fail(FPNMT_ERR_STATE, "submit: this lane still holds a batch (call fpnmt_collect first)");
+  if (!images) return fail(FPNMT_ERR_INVALID, "images is NULL");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  if (!lane_stream_) {
+    FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&lane_stream_, cudaStreamNonBlocking));
+    FPNMT_CUDA_OK(cudaEventCreateWithFlags(&lane_in_ev_, cudaEventDisableTiming));
+    FPNMT_CUDA_OK(cudaEventCreateWithFlags(&lane_out_ev_, cudaEventDisableTiming));
+  }
+  if (!on_host) {
+    FPNMT_CUDA_OK(cudaEventRecord(lane_in_ev_, caller));
+    FPNMT_CUDA_OK(cudaStreamWaitEvent(lane_stream_, lane_in_ev_, 0));
+  }
+  RC(encode(images, on_host, nullptr, lane_stream_, false));
+  if (early_stop) {
+    lane_state_ = 2;
+    return 0;
+  }
+  RC(decode(nullptr, nullptr, 0, 0, nullptr, lane_stream_));
+  lane_state_ = 1;
+  return 0;
+}
+
+int Engine::collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_t caller) {
+  if (lane_state_ == 0) return fail(FPNMT_ERR_STATE, "collect: nothing was submitted on this lane");
+  FPNMT_CUDA_OK(cudaSetDevice(dev_));
+  const int B = cfg_.batch, T = cfg_.max_len;
+  const int st = lane_state_;
+  lane_state_ = 0;
+  if (st == 2) {
+    RC(decode(out_ids, out_len, on_host, 1, nullptr, lane_stream_));
+  } else {
+    const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (out_ids) FPNMT_CUDA_OK(cudaMemcpyAsync(out_ids, bs_.out_ids, (size_t)B * T * 4, kind, lane_stream_));
+    if (out_len) FPNMT_CUDA_OK(cudaMemcpyAsync(out_len, bs_.out_len, (size_t)B * 4, kind, lane_stream_));
+  }
+  if (on_host) {
+    FPNMT_CUDA_OK(cudaStreamSynchronize(lane_stream_));
+  } else {
+    FPNMT_CUDA_OK(cudaEventRecord(lane_out_ev_, lane_stream_));
+    FPNMT_CUDA_OK(cudaStreamWaitEvent(caller, lane_out_ev_, 0));
+  }
+  return 0;
 }
 
 // --------------------------------------------------------------------------------------------- profiling

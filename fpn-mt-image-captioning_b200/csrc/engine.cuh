@@ -75,9 +75,16 @@ class Engine {
   int stage_images(const float* host_images, int slot);
   int generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop, float* step_scores,
                       cudaStream_t s);
+  // Lane interface (fpnmt_submit / fpnmt_collect): one batch in flight per engine on the engine's own stream, so that several
+  // engines ("lanes") of one handle overlap the throughput-bound encode of one batch with the latency-bound decode of another.
+  int submit(const float* images, int on_host, int early_stop, cudaStream_t caller);
+  int collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_t caller);
   int64_t launches = 0;
 
  private:
+  cudaStream_t lane_stream_ = nullptr;
+  cudaEvent_t lane_in_ev_ = nullptr, lane_out_ev_ = nullptr;
+  int lane_state_ = 0;                    // 0 idle, 1 = fixed-length batch enqueued, 2 = encode enqueued, early-stop decode runs in collect()
   fpnmt_config cfg_;
   int dev_;
   int num_sms_ = 148;

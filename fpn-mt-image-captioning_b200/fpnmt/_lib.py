@@ -27,7 +27,7 @@ class FpnmtConfig(C.Structure):
         "backbone", "image_size", "batch", "beam", "vocab", "max_len", "num_layers", "d_model", "num_heads", "dff",
         "precision", "score_mode", "start_id", "end_id", "true_beam", "use_graphs", "kernel_opts", "cache_mode",
         "decode_path")] + [("length_penalty", C.c_float), ("finished_beams", C.c_int32), ("dec_groups", C.c_int32),
-                           ("reserved", C.c_int32 * 2)]
+                           ("lanes", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class FpnmtError(RuntimeError):
@@ -56,8 +56,12 @@ SIGNATURES = {
     "fpnmt_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "fpnmt_profile": (_i, [_vp, _i, C.c_char_p, C.c_size_t]),
     "fpnmt_launch_count": (C.c_int64, [_vp]),
+    "fpnmt_lanes": (_i, [_vp]),
+    "fpnmt_submit": (_i, [_vp, _i, _vp, _i, _i, _vp]),
+    "fpnmt_collect": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "fpnmt_op_conv2d": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "fpnmt_op_preprocess": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "fpnmt_op_decode_jpeg": (_i, [_i, C.POINTER(_vp), C.POINTER(C.c_size_t), _i, _i, _vp, _vp, _vp]),
     "fpnmt_op_dense": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
 }
 

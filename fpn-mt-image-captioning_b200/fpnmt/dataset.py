@@ -50,6 +50,17 @@ KERAS_DEFAULT_FILTERS = '!"#$%&()*+,-./:;<=>?@[\\]^_`{|}~\t\n'
 REFERENCE_FILTERS = '!"#$%&()*+-/:;=?@[\\]^_`{|}~ '      # dataset.py:60 (keeps '.', ',', '<', '>')
 
 
+def load_images_gpu(img_paths, size: int = C.IMAGE_INPUT_SIZE, device: int = 0):
+    """dataset.py:19-26 for a list of JPEG files on the GPU: read_file on the host, decode_jpeg + resize + preprocess_input on
+    the device (nvJPEG + k_preprocess).  Returns float32 (n, size, size, 3) on the device."""
+    from .engine import decode_jpeg
+    data = []
+    for p in img_paths:
+        with open(p, "rb") as f:
+            data.append(f.read())
+    return decode_jpeg(data, size=size, device=device)
+
+
 class Tokenizer:
     """The part of keras.preprocessing.text.Tokenizer the hot path uses (pipeline.py:19,89-90,169,188), with Keras'
     semantics for the two constructor arguments the reference sets (dataset.py:58-60, restored from the JSON config by

@@ -43,10 +43,12 @@ class Engine:
                  score_mode: str = "log", start_id: int = cfg.START_ID, end_id: int = cfg.END_ID,
                  true_beam: bool = False, use_graphs: bool = True, device: int = 0, opts: Sequence[str] = (),
                  cache_mode: str = "ancestry", decode_path: str = "auto", length_penalty: float = 0.0,
-                 finished_beams: bool = False, dec_groups: int = 0, _exp: int = 0):
+                 finished_beams: bool = False, dec_groups: int = 0, lanes: int = 1, _exp: int = 0):
         """opts: names from _lib.OPT_BITS (e.g. "no_xattn") - each turns one fused kernel back into its unfused equivalent;
         cache_mode "ancestry" | "physical"; decode_path "auto" (today: the per-operator chain) | "chain" | "fused" (one
-        dstep_kernel launch runs every layer, the vocabulary projection and the beam tail of all steps); length_penalty / finished_beams: flagged extensions, 0 = reference."""
+        dstep_kernel launch runs every layer, the vocabulary projection and the beam tail of all steps); length_penalty / finished_beams: flagged extensions, 0 = reference;
+        lanes: batches in flight for `generate_stream` (each lane is a complete engine on the same GPU; 2 overlaps the encoder
+        of batch i+1 with the decode of batch i)."""
         if not torch.cuda.is_available():
             raise RuntimeError("fpnmt.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -69,6 +71,8 @@ class Engine:
             c.kernel_opts |= _lib.OPT_BITS[o]
         c.cache_mode, c.decode_path = _lib.CACHE_IDS[cache_mode], _lib.DECODE_IDS[decode_path]
         c.length_penalty, c.finished_beams, c.dec_groups = float(length_penalty), int(finished_beams), int(dec_groups)
+        c.lanes = int(lanes)
+        self.lanes = max(1, int(lanes))
         c.reserved[0] = int(_exp)          # developer A/B switches of the fused decoder (dstep.cuh), 0 in product use
         self._h = C.c_void_p()
         torch.cuda.init()
@@ -201,20 +205,67 @@ class Engine:
                                                   int(early_stop), None, _stream_ptr(self.device)))
         return ids, lens
 
-    def generate_stream(self, batches, early_stop: bool = True):
-        """Captions for an iterable of HOST batches with the copy of batch i+1 overlapped with the compute of batch i
-        (the tf.data prefetch of dataset.py:92).  Yields (ids, lens) host tensors per batch, in order."""
+    def submit(self, lane: int, images, early_stop: bool = False):
+        """Enqueue one whole batch on lane `lane` (fpnmt_submit) and return at once.  Returns a keep-alive object: the images
+        must stay valid until `collect(lane)`."""
+        ptr, on_host, keep = self._images_nocopy(images)
+        _lib.check(self.lib.fpnmt_submit(self._h, int(lane), ptr, on_host, int(early_stop), _stream_ptr(self.device)))
+        return keep
+
+    def collect(self, lane: int, to_host: bool = True):
+        """Result of the batch submitted on `lane` (fpnmt_collect): ids (B,T) int32 zero-padded, lengths (B,)."""
+        if to_host:
+            ids = torch.empty((self.batch, self.max_len), dtype=torch.int32).pin_memory()
+            lens = torch.empty((self.batch,), dtype=torch.int32).pin_memory()
+        else:
+            ids = torch.empty((self.batch, self.max_len), dtype=torch.int32, device=self.device)
+            lens = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.fpnmt_collect(self._h, int(lane), ids.data_ptr(), lens.data_ptr(), int(to_host),
+                                          _stream_ptr(self.device)))
+        return ids, lens
+
+    def _images_nocopy(self, images):
+        """(pointer, on_host, keepalive) for submit: host batches go as they are (the lane copies them on its own stream),
+        device batches are used in place."""
+        return self._images(images)
+
+    def generate_stream(self, batches, early_stop: bool = True, to_host: bool = True):
+        """Captions for an iterable of batches (HOST tensors: pinned memory makes the copies asynchronous; or device tensors),
+        yielded as (ids, lens) per batch, in order.  With `lanes` >= 2 the batches go round-robin through the lanes
+        (fpnmt_submit / fpnmt_collect): host->device copy, encoder and decode of up to `lanes` batches are in flight at once, so
+        the encoder of batch i+1 runs under the decode of batch i; results are identical to `generate` batch by batch.  With one
+        lane: the double-buffered input copy of fpnmt_stage_images / fpnmt_generate_staged (the tf.data prefetch of
+        dataset.py:92)."""
         it = iter(batches)
+        if self.lanes >= 2:
+            L, pending, i = self.lanes, [], 0
+            for b in it:
+                if len(pending) == L:
+                    lane, _keep = pending.pop(0)
+                    yield self.collect(lane, to_host=to_host)
+                lane = i % L
+                pending.append((lane, self.submit(lane, b, early_stop=early_stop)))
+                i += 1
+            for lane, _keep in pending:
+                yield self.collect(lane, to_host=to_host)
+            return
         try:
-            keep = [self.stage(next(it), 0), None]
+            first = next(it)
         except StopIteration:
             return
+        if isinstance(first, torch.Tensor) and first.device.type == "cuda":
+            b = first
+            while b is not None:
+                yield self.generate(b, early_stop=early_stop, to_host=to_host)
+                b = next(it, None)
+            return
+        keep = [self.stage(first, 0), None]
         i = 0
         while True:
             nxt = next(it, None)
             if nxt is not None:
                 keep[(i + 1) & 1] = self.stage(nxt, (i + 1) & 1)
-            yield self.generate_staged(i & 1, early_stop=early_stop, to_host=True)
+            yield self.generate_staged(i & 1, early_stop=early_stop, to_host=to_host)
             if nxt is None:
                 return
             i += 1
@@ -295,3 +346,24 @@ def preprocess(images_u8: torch.Tensor, size: int = cfg.IMAGE_INPUT_SIZE) -> tor
     out = torch.empty((n, size, size, 3), dtype=torch.float32, device=x.device)
     _lib.check(lib.fpnmt_op_preprocess(x.device.index or 0, x.data_ptr(), n, h, w, size, out.data_ptr(), _stream_ptr(x.device)))
     return out
+
+
+def decode_jpeg(jpegs: Sequence[bytes], size: int = cfg.IMAGE_INPUT_SIZE, device: int = 0, return_sizes: bool = False):
+    """GPU `load_image` for a batch of encoded JPEG files (dataset.py:19-26): nvJPEG decode (channels=3) -> bilinear resize
+    (TF2 half-pixel, no antialias) -> x / 127.5 - 1.  Returns float32 (n, size, size, 3) on the device, ready for
+    `Engine.encode` / `generate`; the decoded RGB images never visit the host."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("fpnmt.decode_jpeg needs a CUDA device; there is no CPU fallback")
+    n = len(jpegs)
+    bufs = [np.frombuffer(b, dtype=np.uint8) for b in jpegs]
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (C.c_size_t * n)(*[b.size for b in bufs])
+    dev = torch.device("cuda", device)
+    out = torch.empty((n, size, size, 3), dtype=torch.float32, device=dev)
+    sizes = np.zeros((n, 2), np.int32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.fpnmt_op_decode_jpeg(device, ptrs, lens, n, size, out.data_ptr(), sizes.ctypes.data_as(C.c_void_p),
+                                            _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()       # the encoded bytes (host) may be released after this
+    return (out, sizes) if return_sizes else out

@@ -86,7 +86,10 @@ typedef struct fpnmt_config {
                             the image stops when its best beam is a finished one.  0 = reference (pipeline.py:143-148:
                             stop the moment the top beam emits <end>, finished lower beams keep decoding)          */
   int32_t dec_groups;    /* DECODE_CHAIN only: cut the batch into this many concurrently decoded chains (0/1 = one) */
-  int32_t reserved[2];
+  int32_t lanes;         /* batches in flight (fpnmt_submit / fpnmt_collect): the handle holds this many complete engines
+                            (own activations, KV cache, beam state, stream) on the one GPU, 0/1 = one.  Two lanes overlap
+                            the throughput-bound encoder of batch i+1 with the latency-bound decode of batch i.            */
+  int32_t reserved[1];
 } fpnmt_config;
 
 typedef struct fpnmt_handle fpnmt_handle;
@@ -155,6 +158,19 @@ FPNMT_API int fpnmt_generate(fpnmt_handle* h, const float* images, int images_on
 FPNMT_API int fpnmt_stage_images(fpnmt_handle* h, const float* host_images, int slot);
 FPNMT_API int fpnmt_generate_staged(fpnmt_handle* h, int slot, int32_t* out_ids, int32_t* out_len, int outputs_on_host,
                                     int early_stop, float* step_scores, void* stream);
+/* Replaces: the caller's loop over batches (utils/pipeline.py:156-175 evaluate; test.py:14-21) with `lanes` batches in
+ * flight.  fpnmt_submit enqueues one whole batch (host->device copy when images_on_host, encoder, decode) on lane `lane`'s
+ * own stream and returns at once; fpnmt_collect hands that batch's result over (outputs as fpnmt_generate; host outputs
+ * synchronise the lane's stream, device outputs make `stream` wait for them).  The image buffer must stay valid until the
+ * matching collect; device images are ordered after the work already enqueued on `stream`.  With early_stop != 0 the
+ * decode needs the host to poll the finished-image counter: submit enqueues the encoder only and collect runs the decode
+ * (the encoder of the batch submitted on another lane meanwhile still overlaps it).  A lane holds one batch at a time:
+ * FPNMT_ERR_STATE on a second submit before collect, or a collect without submit.  Results are bit-identical to
+ * fpnmt_generate on the same images (same kernels, same order per lane).  Typical loop, L = fpnmt_lanes(h):
+ *   for i: if (i >= L) collect(i % L, ...batch i-L...); submit(i % L, batch i);   then collect the last L. */
+FPNMT_API int fpnmt_lanes(fpnmt_handle* h);
+FPNMT_API int fpnmt_submit(fpnmt_handle* h, int lane, const float* images, int images_on_host, int early_stop, void* stream);
+FPNMT_API int fpnmt_collect(fpnmt_handle* h, int lane, int32_t* out_ids, int32_t* out_len, int outputs_on_host, void* stream);
 /* Same, from an encoder output already in the engine (after fpnmt_encode) — the decode half only. */
 FPNMT_API int fpnmt_decode(fpnmt_handle* h, int32_t* out_ids, int32_t* out_len, int outputs_on_host, int early_stop,
                  float* step_scores, void* stream);
@@ -178,6 +194,14 @@ FPNMT_API int fpnmt_op_conv2d(int device, int precision, const float* x, int N, 
  * half-pixel centres, no antialias — followed by mobilenet_v2.preprocess_input (x / 127.5 - 1).
  * images_hwc DEVICE uint8 [N, H, W, 3]; out DEVICE float32 NHWC [N, S, S, 3] in [-1, 1] (the layout fpnmt_encode takes). */
 FPNMT_API int fpnmt_op_preprocess(int device, const uint8_t* images_hwc, int N, int H, int W, int S, float* out, void* stream);
+
+/* Replaces: dataset.load_image as a whole (dataset.py:19-26) for a batch of JPEG byte strings: tf.io.read_file's result ->
+ * tf.image.decode_jpeg(channels=3) -> resize to (S, S) -> x / 127.5 - 1.  jpegs: n HOST pointers to the encoded files,
+ * lengths their byte counts; decode runs on the GPU (nvJPEG), the RGB image never visits the host; out DEVICE float32 NHWC
+ * [n, S, S, 3]; sizes_out optional HOST int32 [n][2] = decoded (height, width).  FPNMT_ERR_INVALID names the first image that
+ * is not a decodable JPEG.  Work is enqueued on `stream`; the encoded bytes must stay valid until it has run. */
+FPNMT_API int fpnmt_op_decode_jpeg(int device, const uint8_t* const* jpegs, const size_t* lengths, int n, int S, float* out,
+                                   int32_t* sizes_out, void* stream);
 
 /* out[r, f] = epilogue( x[r, :] @ kernel[:, f] + bias[f] [+ residual[r, f]] ) with the skinny-row Dense kernel of the
  * decoder step (tf.keras.layers.Dense, models/transformer.py:117-122, 165-168, 211-214, 357): x DEVICE float32 [R, K];
