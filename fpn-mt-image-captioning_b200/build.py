@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfpnmt.so")
-SOURCES = ["api.cu", "engine.cu", "igemm.cu", "tgemm.cu", "xattn.cu", "dstep.cu", "stem.cu", "tensormap.cu", "elementwise.cu", "attention.cu", "beam.cu", "jpeg.cu"]
+SOURCES = ["api.cu", "engine.cu", "igemm.cu", "tgemm.cu", "xattn.cu", "dstep.cu", "stem.cu", "tensormap.cu", "elementwise.cu", "attention.cu", "beam.cu", "jpeg.cu", "dlapi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -27,7 +27,8 @@ def _stamp() -> str:
     for f in sorted(os.listdir(CSRC)):
         if f.endswith((".cu", ".cuh")):
             h.update(open(os.path.join(CSRC, f), "rb").read())
-    h.update(open(os.path.join(HERE, "..", "include", "fpnmt.h"), "rb").read())
+    for hdr in ("fpnmt.h", "fpnmt_dlpack.h"):
+        h.update(open(os.path.join(HERE, "..", "include", hdr), "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
@@ -60,7 +61,7 @@ def build(force: bool = False, verbose: bool = True, dbg_stamps: bool = False) -
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(cc, SOURCES))
     cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-                                                 "-lnvjpeg_static", "-lculibos"]
+                                                 "-lnvjpeg_static", "-lculibos", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -130,6 +130,15 @@ FPNMT_API int fpnmt_decode_logits(fpnmt_handle* h, const float* memory, const in
   CHECK_H(h);
   return h->eng->decode_logits(memory, tokens, t, logits_out, (cudaStream_t)stream);
 }
+FPNMT_API int fpnmt_decode_hidden(fpnmt_handle* h, const float* memory, const int32_t* tokens, int t, float* hidden_out,
+                                  void* stream) {
+  CHECK_H(h);
+  if (!hidden_out) {
+    set_last_error("decode_hidden: hidden_out is NULL");
+    return FPNMT_ERR_INVALID;
+  }
+  return h->eng->decode_logits(memory, tokens, t, nullptr, (cudaStream_t)stream, hidden_out);
+}
 FPNMT_API int fpnmt_beam_step(fpnmt_handle* h, const float* logits, const float* scores_in, int32_t* parent, int32_t* token,
                     float* scores_out, void* stream) {
   CHECK_H(h);

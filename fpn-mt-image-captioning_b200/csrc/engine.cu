@@ -1539,7 +1539,8 @@ __global__ void k_forced_tail(BeamState st, const float* __restrict__ logits, co
   const int b = blockIdx.x;
   const float* src = logits + (size_t)(b * st.N) * st.V;
   float* dst = out + ((size_t)b * tlen + t) * st.V;
-  for (int i = threadIdx.x; i < st.V; i += blockDim.x) dst[i] = src[i];
+  if (out)
+    for (int i = threadIdx.x; i < st.V; i += blockDim.x) dst[i] = src[i];
   if (threadIdx.x < st.N && t + 1 < tlen) st.last_tok[b * st.N + threadIdx.x] = forced[(size_t)b * tlen + t + 1];
 }
 __global__ void k_forced_init(BeamState st, const int* __restrict__ forced, int tlen) {
@@ -1550,6 +1551,17 @@ __global__ void k_forced_init(BeamState st, const int* __restrict__ forced, int 
   for (size_t j = i; j < (size_t)2 * rows * st.T; j += (size_t)gridDim.x * blockDim.x)
     st.anc[0][j] = (int)((j / st.T) % rows);   // identity ancestry in both buffers
 }
+// teacher-forced hidden states: beam-0 row of the last decoder layer's output -> hidden_out[b][t][:]
+__global__ void k_forced_hidden(Act x, const int* __restrict__ step, int N, int tlen, float* __restrict__ out) {
+  const int t = *step, b = blockIdx.x;
+  const bf16* row = x.p + (size_t)(b * N) * x.ld;
+  float* dst = out + ((size_t)b * tlen + t) * x.C;
+  for (int i = threadIdx.x; i < x.C; i += blockDim.x) {
+    float v = __bfloat162float(row[i]);
+    if (x.lo) v += __bfloat162float(row[x.lo + i]);
+    dst[i] = v;
+  }
+}
 __global__ void k_step_inc(int* step) { *step += 1; }
 __global__ void k_anc_identity(int* anc, int rows, int T) {
   const size_t n = (size_t)2 * rows * T;
@@ -1557,9 +1569,17 @@ __global__ void k_anc_identity(int* anc, int rows, int T) {
     anc[j] = (int)((j / T) % rows);
 }
 
-int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s) {
+int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s, float* hidden_out) {
   if (!finalized_) return fail(FPNMT_ERR_STATE, "decode_logits before finalize_weights");
   if (t < 1 || t > cfg_.max_len) return fail(FPNMT_ERR_INVALID, "decode_logits: t out of range");
+  if (!tokens || (!logits_out && !hidden_out)) return fail(FPNMT_ERR_INVALID, "decode_logits: NULL tokens / output");
+  const Tensor* last = nullptr;
+  if (hidden_out) {
+    auto it = taps_.find("dec" + std::to_string(cfg_.num_layers - 1) + "_out3");
+    if (it == taps_.end())
+      return fail(FPNMT_ERR_STATE, "decode_hidden: the fused decoder keeps layer outputs only with FPNMT_OPT_DSTEP_TAPS (or use decode_path = chain)");
+    last = &it->second;
+  }
   FPNMT_CUDA_OK(cudaSetDevice(dev_));
   const int R = cfg_.batch * cfg_.beam;
   if (memory) RC(launch_f32_to_act(memory, enc_out_.pixels(), cfg_.d_model, enc_out_.a, s));
@@ -1578,6 +1598,10 @@ int Engine::decode_logits(const float* memory, const int32_t* tokens, int t, flo
       launches += 1;
     } else {
       RC(run_program(step_forced_prog_, s));
+    }
+    if (last) {
+      k_forced_hidden<<<cfg_.batch, 128, 0, s>>>(last->a, bs_.step, cfg_.beam, t, hidden_out);
+      launches += 1;
     }
     k_forced_tail<<<cfg_.batch, 256, 0, s>>>(bs_, logits_, tokens, t, logits_out);
     k_step_inc<<<1, 1, 0, s>>>(bs_.step);
@@ -1644,7 +1668,27 @@ int Engine::decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_st
     // runs across step boundaries)
     if (!loop_graph_) {
       Program loop;
-      for (int t = 0; t < T; ++t) loop.insert(loop.end(), step_prog_.begin(), step_prog_.end());
+      Program one = step_prog_;
+#ifdef FPNMT_DBG_STAMPS   // developer build only: leave ops out of the timed loop (timing attribution; results are garbage)
+      if (const char* sk = getenv("FPNMT_SKIP")) {
+        Program kept;
+        for (auto& op : one) {
+          bool skip = false;
+          std::string list = sk;
+          size_t pos = 0;
+          while (pos <= list.size()) {
+            size_t c = list.find(',', pos);
+            if (c == std::string::npos) c = list.size();
+            const std::string tok = list.substr(pos, c - pos);
+            if (!tok.empty() && op.name.find(tok) != std::string::npos) skip = true;
+            pos = c + 1;
+          }
+          if (!skip) kept.push_back(op);
+        }
+        one = kept;
+      }
+#endif
+      for (int t = 0; t < T; ++t) loop.insert(loop.end(), one.begin(), one.end());
       RC(capture(loop, &loop_graph_));
     }
     FPNMT_CUDA_OK(cudaGraphLaunch(loop_graph_, s));

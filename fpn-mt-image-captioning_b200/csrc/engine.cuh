@@ -60,7 +60,7 @@ class Engine {
   int encode(const float* images, int on_host, float* memory_out, cudaStream_t s, bool cnn_only = false);
   int features(const float* images, int on_host, float* const out5[5], cudaStream_t s);
   int get_tap(const char* name, float* out, size_t cap, size_t* count, cudaStream_t s);
-  int decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s);
+  int decode_logits(const float* memory, const int32_t* tokens, int t, float* logits_out, cudaStream_t s, float* hidden_out = nullptr);
   int beam_step(const float* logits, const float* scores_in, int32_t* parent, int32_t* token, float* scores_out,
                 cudaStream_t s);
   int decode(int32_t* out_ids, int32_t* out_len, int on_host, int early_stop, float* step_scores, cudaStream_t s);
@@ -79,6 +79,8 @@ class Engine {
   // engines ("lanes") of one handle overlap the throughput-bound encode of one batch with the latency-bound decode of another.
   int submit(const float* images, int on_host, int early_stop, cudaStream_t caller);
   int collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_t caller);
+  const fpnmt_config& config() const { return cfg_; }
+  int device() const { return dev_; }
   int64_t launches = 0;
 
  private:

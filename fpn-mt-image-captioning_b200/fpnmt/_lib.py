@@ -65,6 +65,54 @@ SIGNATURES = {
     "fpnmt_op_dense": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
 }
 
+
+
+# ---- DLPack (include/fpnmt_dlpack.h): the `_dl` entry points take `const DLTensor*` --------------------------------------
+class DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+
+class DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", DLDevice), ("ndim", C.c_int32), ("dtype", DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+_dlp = C.POINTER(DLTensor)
+SIGNATURES.update({
+    "fpnmt_decode_hidden": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "fpnmt_set_weight_dl": (_i, [_vp, C.c_char_p, _dlp]),
+    "fpnmt_encode_dl": (_i, [_vp, _dlp, _dlp, _vp]),
+    "fpnmt_features_dl": (_i, [_vp, _dlp, C.POINTER(_dlp), _vp]),
+    "fpnmt_decode_logits_dl": (_i, [_vp, _dlp, _dlp, _dlp, _vp]),
+    "fpnmt_decode_hidden_dl": (_i, [_vp, _dlp, _dlp, _dlp, _vp]),
+    "fpnmt_generate_dl": (_i, [_vp, _dlp, _dlp, _dlp, _i, _dlp, _vp]),
+    "fpnmt_comm_unique_id": (_i, [_vp]),
+    "fpnmt_comm_create": (_i, [_i, _i, _vp, _i, C.POINTER(_vp)]),
+    "fpnmt_comm_destroy": (_i, [_vp]),
+    "fpnmt_allgather_ids": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "fpnmt_allgather_ids_dl": (_i, [_vp, _dlp, _dlp, _dlp, _dlp, _vp]),
+})
+
+
+def dl_tensor(obj):
+    """(pointer to the DLTensor inside the DLPack capsule of `obj`, keep-alive).  `obj` is anything with `__dlpack__`
+    (torch / numpy >= 1.23 / cupy ...): the pointer is the `dl_tensor` member that starts the capsule's DLManagedTensor."""
+    if obj is None:
+        return None, None
+    try:
+        cap = obj.__dlpack__()
+    except TypeError:
+        cap = obj.__dlpack__(stream=None)
+    get = C.pythonapi.PyCapsule_GetPointer
+    get.restype, get.argtypes = C.c_void_p, [C.py_object, C.c_char_p]
+    ptr = get(cap, b"dltensor")
+    return C.cast(ptr, _dlp), (cap, obj)
+
+
 _lib = None
 
 

@@ -37,10 +37,61 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local, world
 
 
-def allgather_captions(ids_local: torch.Tensor, lens_local: torch.Tensor, world: Optional[int] = None
-                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+class Communicator:
+    """The library's own NCCL communicator (fpnmt_comm_*, include/fpnmt_dlpack.h): the all-gather of the caption ids without
+    torch.distributed on the data path.  Bootstrap like NCCL: rank 0 makes the 128-byte unique id, `exchange(id_bytes)` hands it
+    to the other ranks (default: torch.distributed's object broadcast when a process group exists; any out-of-band channel
+    works - a file, a socket, MPI)."""
+
+    def __init__(self, world: int, rank: int, device: int, exchange=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self._check = _lib.check
+        self.world, self.rank, self.device = world, rank, device
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(self.lib.fpnmt_comm_unique_id(buf))
+        uid = bytes(buf)
+        if world > 1:
+            if exchange is None:
+                box = [uid]
+                dist.broadcast_object_list(box, src=0)
+                uid = box[0]
+            else:
+                uid = exchange(uid)
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._c = C.c_void_p()
+        _lib.check(self.lib.fpnmt_comm_create(world, rank, buf, device, C.byref(self._c)))
+
+    def allgather(self, ids_local: torch.Tensor, lens_local: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        b, t = ids_local.shape
+        ids_local, lens_local = ids_local.contiguous(), lens_local.contiguous()
+        all_ids = torch.empty((self.world * b, t), dtype=torch.int32, device=ids_local.device)
+        all_len = torch.empty((self.world * b,), dtype=torch.int32, device=ids_local.device)
+        self._check(self.lib.fpnmt_allgather_ids(self._c, ids_local.data_ptr(), lens_local.data_ptr(), b, t, all_ids.data_ptr(),
+                                                 all_len.data_ptr(), torch.cuda.current_stream(ids_local.device).cuda_stream))
+        return all_ids, all_len
+
+    def close(self):
+        if getattr(self, "_c", None) and self._c.value:
+            self.lib.fpnmt_comm_destroy(self._c)
+            self._c.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def allgather_captions(ids_local: torch.Tensor, lens_local: torch.Tensor, world: Optional[int] = None,
+                       comm: Optional[Communicator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-gather (B_local,T) int32 ids and (B_local,) int32 lengths from every rank (equal B_local) into
-    (world*B_local, T) / (world*B_local,), rank-major — one packed collective."""
+    (world*B_local, T) / (world*B_local,), rank-major — one collective: the library's own NCCL communicator when `comm` is given
+    (GPU runs), else torch.distributed (gloo in the CPU tests)."""
+    if comm is not None and comm.world > 1:
+        return comm.allgather(ids_local, lens_local)
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return ids_local, lens_local
     world = world or dist.get_world_size()

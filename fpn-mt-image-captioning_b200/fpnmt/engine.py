@@ -150,6 +150,18 @@ class Engine:
                                                 _stream_ptr(self.device)))
         return out
 
+    def decode_hidden(self, memory, tokens) -> torch.Tensor:
+        """Decoder.call(x, enc_output, False, mask, None) (transformer.py:321-341) -> last decoder layer's output (B,t,d)."""
+        tok = _as_cuda(tokens, torch.int32, self.device)
+        t = int(tok.shape[1])
+        mem_ptr = None
+        if memory is not None:
+            mem = _as_cuda(memory, torch.float32, self.device)
+            mem_ptr = mem.data_ptr()
+        out = torch.empty((self.batch, t, self.d_model), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.fpnmt_decode_hidden(self._h, mem_ptr, tok.data_ptr(), t, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
     def beam_step(self, logits, scores) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """One decode-tail step (pipeline.py:115-141) on caller logits (B*N,V) and scores (B*N,)."""
         lg = _as_cuda(logits, torch.float32, self.device)

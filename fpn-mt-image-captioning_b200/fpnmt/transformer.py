@@ -89,15 +89,26 @@ class Encoder:
 class Decoder:
     """transformer.py:306-341.  `decoder(x, enc_output, training, look_ahead_mask, padding_mask)`.
 
-    The CUDA decoder is fused with `final_layer`; this object exposes the pre-softmax logits path through
-    `Transformer.__call__` and raises if called on its own for hidden states (not a hot-path operation)."""
+    Returns (hidden states (B,t,d_model) of the last decoder layer, None): computed position by position with the KV-cached
+    step program (the causal mask is implicit), read out through fpnmt_decode_hidden.  The attention-weights dict
+    (transformer.py:337-338, only consumed by the never-called plot_attention_weights) is not produced: SURVEY §8b1."""
 
-    def __init__(self, num_layers, d_model, num_heads, dff, target_vocab_size, rate=0.1, max_position=0, max_seq_len=12):
-        self.d_model, self.num_layers = d_model, num_layers
+    def __init__(self, num_layers, d_model, num_heads, dff, target_vocab_size, rate=0.1, max_position=0, max_seq_len=12,
+                 _cache=None):
+        self.d_model, self.num_layers, self.max_seq_len = d_model, num_layers, max_seq_len
         self.pos_encoding = raw_positional_encoding(max_seq_len + max_position, d_model)
+        self._cache = _cache
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError("Decoder hidden states are not exposed; call Transformer(inp, tar, False, mask)")
+    def __call__(self, x, enc_output, training=False, look_ahead_mask=None, padding_mask=None):
+        if training:
+            raise NotImplementedError("inference-only build: training=True is out of scope")
+        if self._cache is None:
+            raise RuntimeError("Decoder needs the engine of its Transformer (construct it through Transformer(...))")
+        x = torch.as_tensor(x)
+        eng = self._cache.get(int(x.shape[0]), 1, max(self.max_seq_len, int(x.shape[1])))
+        return eng.decode_hidden(enc_output, x), None
+
+    call = __call__
 
 
 class Transformer:
@@ -116,7 +127,8 @@ class Transformer:
         self._cache = _EngineCache(weights, backbone, num_layers, d_model, num_heads, dff, target_vocab_size, max_seq_len,
                                    precision, score_mode, device, start_id, end_id, use_graphs)
         self.encoder = Encoder(num_layers, d_model, num_heads, dff, input_vocab_size, rate, _cache=self._cache)
-        self.decoder = Decoder(num_layers, d_model, num_heads, dff, target_vocab_size, rate, max_position, max_seq_len)
+        self.decoder = Decoder(num_layers, d_model, num_heads, dff, target_vocab_size, rate, max_position, max_seq_len,
+                               _cache=self._cache)
         self.final_layer = ("transformer/final_layer/kernel", "transformer/final_layer/bias")
 
     def __call__(self, inp, tar, training, look_ahead_mask):

@@ -134,6 +134,12 @@ FPNMT_API int fpnmt_get_tap(fpnmt_handle* h, const char* name, float* out, size_
 FPNMT_API int fpnmt_decode_logits(fpnmt_handle* h, const float* memory, const int32_t* tokens, int t, float* logits_out,
                         void* stream);
 
+/* Replaces: Decoder.call(x, enc_output, training=False, look_ahead_mask, padding_mask) (models/transformer.py:321-341): the
+ * output of the last decoder layer (before final_layer) for teacher-forced tokens; arguments as fpnmt_decode_logits,
+ * hidden_out DEVICE float32 [batch, t, d_model].  (The attention-weights dict is not returned: SURVEY §8b1.) */
+FPNMT_API int fpnmt_decode_hidden(fpnmt_handle* h, const float* memory, const int32_t* tokens, int t, float* hidden_out,
+                                  void* stream);
+
 /* Replaces: the body of the decode loop, utils/pipeline.py:115-141, on caller-provided logits (the decode-tail
  * kernels alone): logits DEVICE float32 [batch*beam, vocab], scores_in DEVICE float32 [batch*beam];
  * outputs DEVICE int32 parent[batch*beam], token[batch*beam], float32 scores_out[batch*beam]. */

@@ -14,24 +14,21 @@ from fpnmt.weights import init_weights     # noqa: E402
 B, N, V, T = 64, 8, 10000, 64
 dev = torch.device("cuda", 0)
 w = init_weights("resnet50", vocab=V, seed=0)
-engs = [Engine(w, backbone="resnet50", batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log", device=0)
-        for _ in range(4)]
+OPTS = tuple(o for o in os.environ.get("DIAG_OPTS", "").split(",") if o)
+LANES = [int(x) for x in os.environ.get("DIAG_LANES", "1,2,3,4").split(",")]
 g = torch.Generator().manual_seed(1234)
 imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).to(dev) for _ in range(2)]
-streams = [torch.cuda.Stream(dev) for _ in range(4)]
+print("opts", OPTS)
+for L in LANES:
+    eng = Engine(w, backbone="resnet50", batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log", device=0, opts=OPTS, lanes=L)
 
-
-def run(n, two):
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(n):
-        k = i % two
-        with torch.cuda.stream(streams[k]):
-            engs[k].generate(imgs[i % 2], early_stop=False, to_host=False)
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / n * 1e3
-
-
-for two in (1, 2, 3, 4, 1, 2, 3, 4):
-    run(8, two)
-    print("%d engines / streams" % two, "%.2f ms per batch" % run(24, two), flush=True)
+    def run(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in eng.generate_stream((imgs[i % 2] for i in range(n)), early_stop=False, to_host=False):
+            pass
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    run(8)
+    print("%d lanes: %.2f ms per batch" % (L, run(32)), flush=True)
+    eng.close()

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_header_symbol(built_lib):
-    hdr = open(os.path.join(ROOT, "include", "fpnmt.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "fpnmt.h")).read() + open(os.path.join(ROOT, "include", "fpnmt_dlpack.h")).read()
     declared = sorted(set(re.findall(r"FPNMT_API\s+[\w\s\*]+?\b(fpnmt_\w+)\s*\(", hdr)))
     assert len(declared) >= 16
     lib = C.CDLL(built_lib)
@@ -24,6 +24,58 @@ def test_library_exports_every_header_symbol(built_lib):
         assert hasattr(lib, name), "libfpnmt.so does not export %s" % name
     from fpnmt import _lib
     assert sorted(_lib.SIGNATURES) == declared, "ctypes prototypes and header out of sync"
+
+
+C_PROBE = r"""
+/* A host with no Python and no torch: dlopen the library, bind by name, walk the error paths that need no GPU. */
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "fpnmt_dlpack.h"
+int main(int argc, char** argv) {
+  void* so = dlopen(argv[1], RTLD_NOW);
+  if (!so) { printf("dlopen: %s\n", dlerror()); return 2; }
+  const char* names[] = {"fpnmt_version", "fpnmt_last_error", "fpnmt_create", "fpnmt_destroy", "fpnmt_set_weight",
+    "fpnmt_finalize_weights", "fpnmt_encode", "fpnmt_features", "fpnmt_decode_logits", "fpnmt_decode_hidden", "fpnmt_beam_step",
+    "fpnmt_generate", "fpnmt_submit", "fpnmt_collect", "fpnmt_lanes", "fpnmt_set_weight_dl", "fpnmt_encode_dl",
+    "fpnmt_generate_dl", "fpnmt_allgather_ids", "fpnmt_allgather_ids_dl", "fpnmt_comm_create", "fpnmt_comm_unique_id",
+    "fpnmt_op_decode_jpeg", "fpnmt_op_preprocess"};
+  for (unsigned i = 0; i < sizeof names / sizeof *names; ++i)
+    if (!dlsym(so, names[i])) { printf("missing %s\n", names[i]); return 3; }
+  const char* (*version)(void) = (const char* (*)(void))dlsym(so, "fpnmt_version");
+  const char* (*last_error)(void) = (const char* (*)(void))dlsym(so, "fpnmt_last_error");
+  int (*create)(const fpnmt_config*, int, fpnmt_handle**) = (int (*)(const fpnmt_config*, int, fpnmt_handle**))dlsym(so, "fpnmt_create");
+  int (*generate_dl)(fpnmt_handle*, const DLTensor*, DLTensor*, DLTensor*, int, DLTensor*, void*) =
+      (int (*)(fpnmt_handle*, const DLTensor*, DLTensor*, DLTensor*, int, DLTensor*, void*))dlsym(so, "fpnmt_generate_dl");
+  int (*allgather)(fpnmt_comm*, const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, void*) =
+      (int (*)(fpnmt_comm*, const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, void*))dlsym(so, "fpnmt_allgather_ids");
+  if (!strstr(version(), "sm_100a")) return 4;
+  fpnmt_handle* h = NULL;
+  if (create(NULL, 0, &h) != FPNMT_ERR_INVALID) return 5;
+  fpnmt_config cfg; memset(&cfg, 0, sizeof cfg);
+  int rc = create(&cfg, 0, &h);                 /* no GPU: ERR_CUDA "no CPU fallback"; GPU: ERR_INVALID (all-zero config) */
+  if (rc != FPNMT_ERR_CUDA && rc != FPNMT_ERR_INVALID) return 6;
+  if (!strlen(last_error())) return 7;
+  if (generate_dl(NULL, NULL, NULL, NULL, 0, NULL, NULL) != FPNMT_ERR_INVALID) return 8;
+  if (allgather(NULL, NULL, NULL, 1, 1, NULL, NULL, NULL) != FPNMT_ERR_INVALID) return 9;
+  printf("ok %d %zu\n", rc, sizeof(fpnmt_config));
+  return 0;
+}
+"""
+
+
+def test_c_host_binds_the_library_without_python(built_lib, tmp_path):
+    """A plain C program (gcc, dlopen) sees the ABI include/*.h declares: symbols, struct size, error codes and messages."""
+    src = tmp_path / "probe.c"
+    src.write_text(C_PROBE)
+    exe = tmp_path / "probe"
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-ldl"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), built_lib], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    from fpnmt import _lib
+    assert r.stdout.split()[0] == "ok" and int(r.stdout.split()[2]) == C.sizeof(_lib.FpnmtConfig)   # ctypes mirror == C struct
 
 
 def test_library_has_blackwell_code(built_lib):
