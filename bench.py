@@ -9,7 +9,7 @@ BASELINE.json: ResNet-50-FPN + Multi-Transformer, beam 8, batch 64, 3x512x512 sy
 random-init weights, V=10000, T=64 decode steps, early stop OFF (fixed work).
 
   value  images/s, inputs already resident in HBM, ids left on the device (+ NCCL all-gather of ids for N>1),
-         through the streaming call with `--lanes` batches in flight per GPU (default 2: the encoder of batch i+1 runs
+         through the streaming call with `--lanes` batches in flight per GPU (default 3: the encoder of batch i+1 runs
          under the decode of batch i; every batch is submitted and collected inside the timed region),
          timed with CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
   one_shot  the same batches one at a time through Engine.generate (the latency of a batch; ids equal to the streamed ones).
@@ -485,7 +485,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="batches in flight per GPU (1 = one batch at a time)")
+    ap.add_argument("--lanes", type=int, default=3, help="batches in flight per GPU (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 throughput leg (parity_mode key)")
     ap.add_argument("--profile-iters", type=int, default=10)

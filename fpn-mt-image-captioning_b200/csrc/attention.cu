@@ -580,14 +580,184 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, SPLIT ? 4 : 8) k_dec_self_atte
     st_act8(out, (size_t)row, h * DH + lane * 8, o);
   }
 }
+static bool g_dec_att_simt = false;   // FPNMT_OPT_DEC_ATT_SIMT: CUDA-core decode self-attention in bf16 mode too
+void set_dec_att_simt(bool v) { g_dec_att_simt = v; }
+
+// ---- bf16 mode: the same attention on mma.sync.m16n8k16 ---------------------------------------------------------------
+// The CUDA-core kernel above is bound by instruction issue, not by HBM (ncu at t = 40: 1 800 instructions per warp, issue
+// slots 55 % busy, DRAM 42 %): per cached position a lane unpacks and multiplies 16 values and takes part in 3 shuffles.
+// Here a warp still owns one (row, head), but the arithmetic is two small tensor-core products per 32-position chunk:
+//   S^T = K_chunk[32 x 64] . q[64]      A = K rows from shared memory (ldmatrix), B = the query in column 0 of an n8 tile
+//   o   = p[32] . V_chunk[32 x 64]      A = the probabilities in row 0 of an m16 tile (bf16 hi + lo parts: two MMAs, so the
+//                                       probabilities keep ~16 mantissa bits), B = V rows (ldmatrix.trans)
+// 7/8 of each MMA is padding - the tensor pipe is idle in this kernel anyway; what matters is ~4x fewer issued instructions.
+// K and V rows of the chunk are staged with cp.async into a 128-byte-row XOR-swizzled tile (conflict-free for both the
+// 16-byte copies and ldmatrix); the new position's K/V (from the QKV projection) is written into the tile directly and
+// appended to the cache.  Online softmax across chunks as before.
+struct __align__(128) DecAttTile {
+  uint4 k[32 * 8];
+  uint4 v[32 * 8];
+};
+
+__global__ void __launch_bounds__(DEC_WARPS * 32, 7) k_dec_self_attention_mma(Act qkv, Act kc0, Act vc0, Act kc1, Act vc1,
+                                                                              const int* __restrict__ anc_base, size_t anc_stride,
+                                                                              const int* __restrict__ step, int rows, int T,
+                                                                              int heads, Act out) {
+  __shared__ DecAttTile s_tile[DEC_WARPS];
+  pdl_launch();
+  pdl_wait();
+  const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+  if (gw >= rows * heads) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int row = gw / heads, h = gw % heads;
+  const int d = heads * DH;
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t sK = smem_u32(s_tile[w].k), sV = smem_u32(s_tile[w].v);
+  const int* anc_e = anc_base + (size_t)row * T;
+  const int* anc_o = anc_e + anc_stride;
+  int a_e[2], a_o[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int pos = c * 32 + lane;
+    a_e[c] = pos < T ? __ldg(anc_e + pos) : 0;
+    a_o[c] = pos < T ? __ldg(anc_o + pos) : 0;
+  }
+  const int t = *step;
+  const bool second = kc1.p != nullptr && (t & 1);      // physical cache mode: odd steps live in the second buffer pair
+  const Act kc = second ? kc1 : kc0, vc = second ? vc1 : vc0;
+  const int* anc = (t & 1) ? anc_o : anc_e;
+  const int a0 = (t & 1) ? a_o[0] : a_e[0], a1 = (t & 1) ? a_o[1] : a_e[1];
+  const bf16* qrow = qkv.p + (size_t)row * qkv.ld + h * DH;
+  // the query as B fragments (k = dims, n = 0): lanes 0..3 hold column 0, every other column is zero
+  uint32_t qb[8];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qb[2 * ks] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * lane) : 0u;
+    qb[2 * ks + 1] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * lane) : 0u;
+  }
+  const uint32_t knew = *reinterpret_cast<const uint32_t*>(qrow + d + 2 * lane);
+  const uint32_t vnew = *reinterpret_cast<const uint32_t*>(qrow + 2 * d + 2 * lane);
+  *reinterpret_cast<uint32_t*>(kc.p + ((size_t)row * T + t) * kc.ld + h * DH + 2 * lane) = knew;     // append to the cache
+  *reinterpret_cast<uint32_t*>(vc.p + ((size_t)row * T + t) * vc.ld + h * DH + 2 * lane) = vnew;
+  float m = -INFINITY, l = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  const int Tk = t + 1;                                  // cached positions 0..t-1 and the new one
+  for (int k0 = 0; k0 < Tk; k0 += 32) {
+    const int kmax = min(32, Tk - k0);
+    const int pos = k0 + lane;
+    const unsigned my_row = pos < t ? (unsigned)((size_t)(pos < 32 ? a0 : pos < 64 ? a1 : anc[pos]) * T + pos) : 0u;
+    // ---- stage the chunk: lane -> (position 4i + lane/8, 16-byte unit lane%8); rows past the new position are zero-filled
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pp = 4 * i + (lane >> 3), u = lane & 7;
+      const unsigned r = __shfl_sync(0xffffffffu, my_row, pp);
+      const int gp = k0 + pp;
+      const uint32_t off = (uint32_t)(pp * 128 + ((u ^ (pp & 7)) << 4));
+      if (gp != t) {
+        cp16(sK + off, kc.p + (size_t)r * kc.ld + h * DH + u * 8, gp < t);
+        cp16(sV + off, vc.p + (size_t)r * vc.ld + h * DH + u * 8, gp < t);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (t >= k0 && t < k0 + 32) {                        // the new position: straight from the registers
+      const int pn = t - k0;
+      const uint32_t off = (uint32_t)(pn * 128 + (((lane >> 2) ^ (pn & 7)) << 4) + (lane & 3) * 4);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sK + off), "r"(knew) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sV + off), "r"(vnew) : "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- scores: lanes with lane % 4 == 0 end up with positions {g, g+8} of each 16-position tile
+    float sc[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mt * 16 < kmax) {
+        const int r = mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a[4];
+          ldsm_x4(a, sK + (uint32_t)(r * 128 + (((ks * 2 + (lane >> 4)) ^ (r & 7)) << 4)));
+          mma_16816(acc, a, qb[2 * ks], qb[2 * ks + 1]);
+        }
+      }
+      sc[2 * mt] = (tq == 0 && mt * 16 + g < kmax) ? acc[0] * 0.125f : -INFINITY;
+      sc[2 * mt + 1] = (tq == 0 && mt * 16 + 8 + g < kmax) ? acc[2] * 0.125f : -INFINITY;
+    }
+    float cmax = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, off));
+    const float mn = fmaxf(m, cmax);
+    const float corr = __expf(m - mn);
+    float psum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sc[i] = __expf(sc[i] - mn);                         // exp(-inf) = 0 for the masked entries
+      psum += sc[i];
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+    l = l * corr + psum;
+    m = mn;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      o[nb][0] *= corr;
+      o[nb][1] *= corr;
+    }
+    // ---- o += p . V: probabilities into row 0 of the A tile (lanes 0..3), split into bf16 hi + lo
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      if (kt * 16 < kmax) {
+        const float x0 = __shfl_sync(0xffffffffu, sc[2 * kt], 8 * tq), x1 = __shfl_sync(0xffffffffu, sc[2 * kt], 8 * tq + 4);
+        const float y0 = __shfl_sync(0xffffffffu, sc[2 * kt + 1], 8 * tq), y1 = __shfl_sync(0xffffffffu, sc[2 * kt + 1], 8 * tq + 4);
+        uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
+        if (lane < 4) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(y0, y1);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(y0 - f1.x, y1 - f1.y);
+          ah[0] = *reinterpret_cast<const uint32_t*>(&h0);
+          ah[2] = *reinterpret_cast<const uint32_t*>(&h1);
+          al[0] = *reinterpret_cast<const uint32_t*>(&l0);
+          al[2] = *reinterpret_cast<const uint32_t*>(&l1);
+        }
+        const int r = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b[4];
+          ldsm_x4_t(b, sV + (uint32_t)(r * 128 + (((np * 2 + (lane >> 4)) ^ (r & 7)) << 4)));
+          mma_16816(o[2 * np], ah, b[0], b[1]);
+          mma_16816(o[2 * np], al, b[0], b[1]);
+          mma_16816(o[2 * np + 1], ah, b[2], b[3]);
+          mma_16816(o[2 * np + 1], al, b[2], b[3]);
+        }
+      }
+    }
+    __syncwarp();                                        // the tile is restaged by the next chunk
+  }
+  if (lane < 4) {                                        // row 0 of the accumulators: dims nb*8 + 2*lane, +1
+    const float inv = 1.f / l;
+    bf16* orow = out.p + (size_t)row * out.ld + h * DH + 2 * lane;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[nb][0] * inv, o[nb][1] * inv);
+      *reinterpret_cast<__nv_bfloat162*>(orow + nb * 8) = v2;
+    }
+  }
+}
+
 int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act vcache2, const int* anc, size_t anc_stride,
                               const int* step, int rows, int T, int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
   if (kcache.lo)
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
                            qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
-  else
+  else if (qkv.lo || out.lo || g_dec_att_simt)
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+                           qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
+  else
+    FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention_mma, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
                            qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
   return 0;
 }

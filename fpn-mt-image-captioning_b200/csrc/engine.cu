@@ -89,6 +89,7 @@ int Engine::init() {
   use_xattn_ = !(c.kernel_opts & FPNMT_OPT_NO_XATTN);
   use_stem_ = !(c.kernel_opts & FPNMT_OPT_NO_STEM);
   use_tgemm_ = !(c.kernel_opts & FPNMT_OPT_NO_TGEMM);
+  set_dec_att_simt((c.kernel_opts & FPNMT_OPT_DEC_ATT_SIMT) != 0);   // process-wide, like the PDL mode
   set_pdl_mode((c.kernel_opts & FPNMT_OPT_NO_PDL) ? 0 : (c.kernel_opts & FPNMT_OPT_PDL_GEMM_ONLY) ? 2 : 1);
   if (c.cache_mode < 0 || c.cache_mode > 1 || c.decode_path < 0 || c.decode_path > 2 || c.dec_groups < 0 || c.length_penalty < 0.f)
     return fail(FPNMT_ERR_INVALID, "bad cache_mode / decode_path / dec_groups / length_penalty");

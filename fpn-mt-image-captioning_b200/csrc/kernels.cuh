@@ -8,6 +8,7 @@ namespace fpnmt {
 // "done once per process" guard would leave a second engine on another GPU of the same process without them).
 int elementwise_set_attributes();
 int attention_set_attributes();
+void set_dec_att_simt(bool v);   // bf16 mode: CUDA-core decode self-attention instead of the mma.sync kernel (A/B, parity tests)
 int beam_set_attributes();
 
 // ---- elementwise.cu -----------------------------------------------------------------------------

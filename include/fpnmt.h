@@ -51,6 +51,7 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
        FPNMT_OPT_KSPLIT2 = 16,       /* split-K over an 8-CTA cluster for the K = 2048 LayerNorm Dense (slower on B200)  */
        FPNMT_OPT_NO_PDL = 32,        /* no programmatic dependent launch (process-wide: the last created engine wins)    */
        FPNMT_OPT_PDL_GEMM_ONLY = 64, /* only the tcgen05 GEMM kernels launch early                                      */
+       FPNMT_OPT_DEC_ATT_SIMT = 256, /* CUDA-core decode self-attention in bf16 mode (instead of the mma.sync kernel)          */
        FPNMT_OPT_DSTEP_TAPS = 128    /* fused decoder: also keep every layer's LayerNorm outputs (fpnmt_get_tap "decL_outK") */ };
 enum { FPNMT_CACHE_ANCESTRY = 0,     /* KV cache never moves; an ancestry table maps (beam, position) -> physical row    */
        FPNMT_CACHE_PHYSICAL = 1 };   /* KV cache rows are gathered by beam parent after every step (bandwidth kernel)    */
