@@ -212,7 +212,8 @@ def run_own(args, wl):
     B, N, V, T = wl["batch"], wl["beam"], wl["vocab"], wl["max_len"]
     w = init_weights(wl["backbone"], vocab=V, seed=0)
     eng = Engine(w, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision=args.precision,
-                 score_mode="log", use_graphs=not args.no_graphs, device=local, lanes=args.lanes)
+                 score_mode="log", use_graphs=not args.no_graphs, device=local, lanes=args.lanes,
+                 opts=tuple(o for o in args.opts.split(",") if o))
     del w
     g = torch.Generator().manual_seed(1234 + rank)
     host_imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).pin_memory() for _ in range(2)]
@@ -485,7 +486,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3, help="batches in flight per GPU (1 = one batch at a time)")
+    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per GPU (1 = one batch at a time)")
+    ap.add_argument("--opts", default="", help="comma-separated fpnmt kernel_opts names (developer A/B, e.g. tgemm_wide)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 throughput leg (parity_mode key)")
     ap.add_argument("--profile-iters", type=int, default=10)

@@ -297,8 +297,14 @@ FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, i
     return FPNMT_ERR_CUDA;
   }
   int rc = tgemm_set_attributes();
+  if (!rc) rc = tgemmw_set_attributes();
   if (rc) return rc;
   const bool split = precision == FPNMT_PREC_BF16X3;
+  const bool wide = force_bn >= 128;          // the wide-row two-CTAs-per-SM kernel (tgemmw.cu)
+  if (wide && !tgemmw_supports(split, residual != nullptr, gamma != nullptr, F, K)) {
+    set_last_error("op_dense: the wide-row kernel needs bf16 precision and a residual only together with LayerNorm");
+    return FPNMT_ERR_INVALID;
+  }
   const size_t ldw = split ? 2 * (size_t)K : (size_t)K;
   std::vector<uint16_t> hw((size_t)F * ldw);
   for (int k = 0; k < K; ++k)
@@ -341,7 +347,9 @@ FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, i
     rc = launch_f32_to_act(residual, R, F, ar, s);
   }
   TgemmOp op;
-  if (!rc)
+  if (!rc && wide)
+    rc = make_tgemmw_op(&op, R, ax, dw, F, K, dbias, act, ao, nullptr, 0, residual ? &ar : nullptr, dg, db, eps, prop.multiProcessorCount);
+  else if (!rc)
     rc = make_tgemm_op(&op, R, ax, dw, F, K, split, dbias, act, ao, nullptr, 0, residual ? &ar : nullptr, dg, db, eps,
                        prop.multiProcessorCount, force_bn);
   if (!rc) rc = tgemm_launch(op, s);

@@ -81,6 +81,7 @@ int Engine::init() {
   num_sms_ = prop.multiProcessorCount;
   RC(igemm_set_attributes());
   RC(tgemm_set_attributes());
+  RC(tgemmw_set_attributes());
   RC(xattn_set_attributes());
   RC(elementwise_set_attributes());
   RC(attention_set_attributes());
@@ -348,8 +349,13 @@ int Engine::add_dense(Program& prog, const std::string& name, const Tensor& in, 
   if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
   const int R = (int)in.pixels();
   TgemmOp op;
-  RC(make_tgemm_op(&op, R, in.a, gw.w, gw.Cout, gw.K, split_, gw.bias, act, out.a, out_f32, ld_f32, res ? &res->a : nullptr,
-                   gamma, beta, 1e-6f, num_sms_, 0, (cfg_.kernel_opts & FPNMT_OPT_KSPLIT2) != 0));
+  const bool want_wide = (cfg_.kernel_opts & FPNMT_OPT_TGEMM_WIDE) || (cfg_.lanes >= 2 && !(cfg_.kernel_opts & FPNMT_OPT_NO_TGEMM_WIDE));
+  if (want_wide && out_f32 == nullptr && tgemmw_supports(split_, res != nullptr, gamma != nullptr, gw.Cout, gw.K))
+    RC(make_tgemmw_op(&op, R, in.a, gw.w, gw.Cout, gw.K, gw.bias, act, out.a, out_f32, ld_f32, res ? &res->a : nullptr, gamma, beta,
+                      1e-6f, num_sms_));
+  else
+    RC(make_tgemm_op(&op, R, in.a, gw.w, gw.Cout, gw.K, split_, gw.bias, act, out.a, out_f32, ld_f32, res ? &res->a : nullptr,
+                     gamma, beta, 1e-6f, num_sms_, 0, (cfg_.kernel_opts & FPNMT_OPT_KSPLIT2) != 0));
   op.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;

@@ -492,6 +492,7 @@ static int launch_bn(const TgemmOp& op, cudaStream_t stream) {
 }
 
 int tgemm_launch(const TgemmOp& op, cudaStream_t stream) {
+  if (op.wide) return tgemmw_launch(op, stream);
   if (op.BN == 32) return launch_bn<32>(op, stream);
   if (op.BN == 64) return launch_bn<64>(op, stream);
   set_last_error("tgemm_launch: unsupported BN");
@@ -556,6 +557,7 @@ int make_tgemm_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K
   p.beta = beta;
   p.eps = eps;
   op->BN = BN;
+  op->wide = 0;
   op->grid = p.ftiles * p.ksplit * rgroups;
   op->cluster = ln ? 4 * p.ksplit : 1;
   op->flops = 2.0 * (double)R * (double)F * (double)K;

@@ -47,7 +47,8 @@ struct TgemmParams {
 struct TgemmOp {
   CUtensorMap tmW, tmX_hi, tmX_lo;
   TgemmParams p;
-  int BN;        // 32 or 64
+  int BN;        // 32 or 64 (tgemm_kernel); 64 or 128 (tgemmw_kernel)
+  int wide;      // 1: tgemmw_kernel (tgemmw.cu)
   int grid;
   int cluster;   // 1, 4 (LayerNorm) or 8 (LayerNorm + split-K)
   double flops;
@@ -61,5 +62,13 @@ int tgemm_set_attributes();
 int make_tgemm_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, bool split, const float* bias, int act,
                   const Act& out, float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta,
                   float eps, int num_sms, int force_bn = 0, bool ksplit2 = false);
+
+// Wide-row, two-CTAs-per-SM variant (tgemmw.cu): BN = 128 rows per CTA, K streamed through a 96 KB ring, bf16 mode only.
+size_t tgemmw_smem_bytes(int BN);
+int tgemmw_launch(const TgemmOp& op, cudaStream_t stream);
+int tgemmw_set_attributes();
+bool tgemmw_supports(bool split, bool has_res, bool ln, int F, int K);
+int make_tgemmw_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, const float* bias, int act, const Act& out,
+                   float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta, float eps, int num_sms);
 
 }  // namespace fpnmt

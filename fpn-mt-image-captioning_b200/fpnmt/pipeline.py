@@ -6,9 +6,10 @@ train.py:24,68,100,104).  `predict` / `evaluate` / `evaluate_img` return exactly
 `predict_batch` is the additive batched entry point.  Training members (`train_step`, `loss`, optimizer,
 checkpoint manager) are out of scope and absent.
 
-Checkpoints: the reference restores a TensorFlow object-graph checkpoint (pipeline.py:38-48).  No TF reader
-exists here; `checkpoint_path` may instead name an `.npz` (or a directory holding `weights.npz`) keyed by the
-same variable paths.  Without one the model is randomly initialised with the reference's distributions.
+Checkpoints: the reference restores a TensorFlow object-graph checkpoint through a CheckpointManager
+(pipeline.py:38-48).  `checkpoint_path` may name such a directory (`checkpoint` state file + `ckpt-N.index/.data-*`, read by
+`fpnmt.checkpoint` without TensorFlow), a checkpoint prefix, or an `.npz` (or a directory holding `weights.npz`) keyed by
+the same variable paths.  Without any of them the model is randomly initialised with the reference's distributions.
 """
 from __future__ import annotations
 
@@ -42,6 +43,13 @@ class Pipeline:
             if os.path.exists(cand):
                 weights = load_weights(cand)
                 print("Latest checkpoint restored!!")                           # pipeline.py:48
+            else:
+                from .checkpoint import latest_checkpoint, load_checkpoint
+                prefix = latest_checkpoint(str(checkpoint_path)) if os.path.isdir(str(checkpoint_path)) else \
+                    (str(checkpoint_path) if os.path.exists(str(checkpoint_path) + ".index") else None)
+                if prefix:                                                      # pipeline.py:46-48 (latest_checkpoint)
+                    weights = load_checkpoint(prefix, backbone)
+                    print("Latest checkpoint restored!!")
         vocab_padded = (self.target_vocab_size + 7) // 8 * 8                   # engine wants vocab % 8 == 0
         self._vocab_padded = vocab_padded
         if weights is None:

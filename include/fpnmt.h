@@ -52,6 +52,11 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
        FPNMT_OPT_NO_PDL = 32,        /* no programmatic dependent launch (process-wide: the last created engine wins)    */
        FPNMT_OPT_PDL_GEMM_ONLY = 64, /* only the tcgen05 GEMM kernels launch early                                      */
        FPNMT_OPT_DEC_ATT_SIMT = 256, /* CUDA-core decode self-attention in bf16 mode (instead of the mma.sync kernel)          */
+       FPNMT_OPT_TGEMM_WIDE = 512,   /* bf16 Dense layers on tgemmw_kernel (128 rows per CTA, two CTAs per SM, TMA-store
+                                        epilogue: least SM time, best when several lanes share the GPU) even with lanes < 2.
+                                        Default: tgemmw_kernel when fpnmt_config.lanes >= 2, else tgemm_kernel (lowest
+                                        latency of a single chain)                                                         */
+       FPNMT_OPT_NO_TGEMM_WIDE = 1024, /* never tgemmw_kernel                                                             */
        FPNMT_OPT_DSTEP_TAPS = 128    /* fused decoder: also keep every layer's LayerNorm outputs (fpnmt_get_tap "decL_outK") */ };
 enum { FPNMT_CACHE_ANCESTRY = 0,     /* KV cache never moves; an ancestry table maps (beam, position) -> physical row    */
        FPNMT_CACHE_PHYSICAL = 1 };   /* KV cache rows are gathered by beam parent after every step (bandwidth kernel)    */
@@ -214,7 +219,8 @@ FPNMT_API int fpnmt_op_decode_jpeg(int device, const uint8_t* const* jpegs, cons
  * decoder step (tf.keras.layers.Dense, models/transformer.py:117-122, 165-168, 211-214, 357): x DEVICE float32 [R, K];
  * kernel HOST float32 (K, F) Keras layout; bias HOST [F] or NULL; residual DEVICE float32 [R, F] or NULL; out DEVICE
  * float32 [R, F].  gamma/beta HOST [F] != NULL (F must be 512): the epilogue is LayerNormalization(epsilon=eps) of
- * (dense + residual) (models/transformer.py:192,198,230,235,241), computed by a 4-CTA cluster. act as fpnmt_op_conv2d. */
+ * (dense + residual) (models/transformer.py:192,198,230,235,241), computed by a 4-CTA cluster. act as fpnmt_op_conv2d.
+ * force_bn: 0 = automatic, 32 / 64 = rows per CTA of tgemm_kernel, 128 = the wide-row kernel of FPNMT_OPT_TGEMM_WIDE. */
 FPNMT_API int fpnmt_op_dense(int device, int precision, const float* x, int R, int K, const float* kernel, int F,
                    const float* bias, int act, const float* residual, const float* gamma, const float* beta, float eps,
                    float* out, int force_bn, void* stream);

@@ -10,7 +10,7 @@ from fpnmt.engine import Engine
 from fpnmt.weights import init_weights
 bb, B, N, V, T = "mobilenet224_1.0", 64, 8, 10000, 64
 w = init_weights(bb, vocab=V, seed=0)
-eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T)
+eng = Engine(w, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, opts=tuple(o for o in os.environ.get("DIAG_OPTS", "").split(",") if o))
 img = (torch.rand(B, 512, 512, 3) * 2 - 1).cuda()
 eng.generate(img, early_stop=False)
 torch.cuda.synchronize()

@@ -155,6 +155,16 @@ DENSE_CASES = [
     ("ln_ffn2_k2048", 512, 2048, 512, 0, True, True, 0),
     ("ln_ragged_rows_40", 40, 512, 512, 0, True, True, 0),
     ("ln_no_residual", 64, 512, 512, 0, False, True, 0),
+    # wide-row kernel (tgemmw.cu, FPNMT_OPT_TGEMM_WIDE): 128 (64) rows per CTA, ring-streamed K, two CTAs per SM; bf16 only
+    ("wide_qkv_1536", 512, 512, 1536, 0, False, False, 128),
+    ("wide_ffn1_leaky_2048", 512, 512, 2048, 2, False, False, 128),
+    ("wide_vocab_10000_multi_rowtile", 1024, 512, 10000, 0, False, False, 128),
+    ("wide_vocab_1000_ragged_rows_192", 192, 512, 1000, 1, False, False, 128),
+    ("wide_rows_40_bn64", 40, 512, 256, 0, False, False, 128),
+    ("wide_ln_o_proj", 512, 512, 512, 0, True, True, 128),
+    ("wide_ln_ffn2_k2048", 512, 2048, 512, 0, True, True, 128),
+    ("wide_ln_ragged_rows_300", 300, 512, 512, 0, True, True, 128),
+    ("wide_ln_rows_40_bn64", 40, 2048, 512, 0, True, True, 128),
 ]
 
 
@@ -163,6 +173,8 @@ DENSE_CASES = [
 def test_tgemm_dense(case, prec, tol):
     from fpnmt.engine import dense
     name, R, K, Fo, act, has_res, ln, fbn = case
+    if fbn >= 128 and prec != "bf16":
+        pytest.skip("the wide-row kernel is a bf16-mode kernel")
     g = torch.Generator().manual_seed(abs(hash(name)) % (2 ** 31))
     x = torch.randn(R, K, generator=g)
     k = (torch.randn(K, Fo, generator=g) / np.sqrt(K)).numpy()
