@@ -211,9 +211,10 @@ def run_own(args, wl):
     dev = torch.device("cuda", local)
     B, N, V, T = wl["batch"], wl["beam"], wl["vocab"], wl["max_len"]
     w = init_weights(wl["backbone"], vocab=V, seed=0)
+    eng_opts = tuple(o for o in args.opts.split(",") if o)
     eng = Engine(w, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision=args.precision,
                  score_mode="log", use_graphs=not args.no_graphs, device=local, lanes=args.lanes,
-                 opts=tuple(o for o in args.opts.split(",") if o))
+                 opts=eng_opts)
     del w
     g = torch.Generator().manual_seed(1234 + rank)
     host_imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).pin_memory() for _ in range(2)]
@@ -252,7 +253,9 @@ def run_own(args, wl):
 
     for i in range(max(args.warmup, 3)):
         step_device(i)
-    run_device(max(args.warmup, 3))
+    # every lane goes through its first use (graph capture + instantiation, pinned staging) before anything is timed
+    n_warm = max(args.warmup, 3, 2 * max(1, args.lanes))
+    run_device(n_warm)
     torch.cuda.synchronize()
     if args.ncu_step:        # `ncu --profile-from-start off ... bench.py --ncu-step`: capture exactly ONE whole step
         torch.cuda.cudart().cudaProfilerStart()
@@ -275,7 +278,7 @@ def run_own(args, wl):
     ms = fd.max_over_ranks(e0.elapsed_time(e1), dev)
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
-    ids_check = out[0]
+    ids_check = out[0].clone()      # the lanes' output buffers are reused by every later call
     # ---- one batch at a time (nothing else in flight): the latency of a batch, and the cross-check of the lanes' results
     k1 = max(2, min(args.steps, 6))
     fd.barrier()
@@ -288,7 +291,7 @@ def run_own(args, wl):
     ms_one = fd.max_over_ranks(e0.elapsed_time(e1), dev) / k1
     lanes_equal = bool(torch.equal(out1[0].cpu(), ids_check.cpu()))      # same last batch, one-shot vs streamed through the lanes
     # ---- end-to-end timing (host buffers)
-    run_host(2)
+    run_host(n_warm)
     torch.cuda.synchronize()
     fd.barrier()
     torch.cuda.synchronize()
@@ -420,7 +423,8 @@ def run_own(args, wl):
     if world == 1 and args.precision == "bf16" and not args.no_parity_mode:
         wp = init_weights(wl["backbone"], vocab=V, seed=0)
         engp = Engine(wp, backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log",
-                      use_graphs=not args.no_graphs, device=local, cache_mode="physical", decode_path="chain")
+                      use_graphs=not args.no_graphs, device=local, cache_mode="physical", decode_path="chain",
+                      opts=eng_opts + (("tgemm_wide",) if eng_lanes >= 2 and "no_tgemm_wide" not in eng_opts else ()))   # the kernels of `eng`
         del wp
         for i in range(3):
             ids_p, _ = engp.generate(dev_imgs[i % 2], early_stop=False, to_host=False)

@@ -22,6 +22,7 @@ using namespace fpnmt;
 struct fpnmt_handle {
   Engine* eng;                   // lane 0: every single-batch entry point runs here
   std::vector<Engine*> lanes;    // lanes[0] == eng; fpnmt_submit / fpnmt_collect address the others
+  cudaEvent_t last_encode = nullptr;   // encoder-done event of the most recent fpnmt_submit (owned by that lane)
 };
 
 extern "C" {
@@ -103,7 +104,9 @@ FPNMT_API int fpnmt_submit(fpnmt_handle* h, int lane, const float* images, int o
     set_last_error("fpnmt_submit: lane out of range (fpnmt_config.lanes)");
     return FPNMT_ERR_INVALID;
   }
-  return h->lanes[lane]->submit(images, on_host, early_stop, (cudaStream_t)stream);
+  const int rc = h->lanes[lane]->submit(images, on_host, early_stop, (cudaStream_t)stream, h->last_encode);
+  if (!rc) h->last_encode = h->lanes[lane]->encode_done_event();
+  return rc;
 }
 FPNMT_API int fpnmt_collect(fpnmt_handle* h, int lane, int32_t* out_ids, int32_t* out_len, int outputs_on_host, void* stream) {
   CHECK_H(h);

@@ -13,6 +13,7 @@
 struct fpnmt_handle {          // same layout as in api.cu
   fpnmt::Engine* eng;
   std::vector<fpnmt::Engine*> lanes;
+  cudaEvent_t last_encode = nullptr;
 };
 
 namespace fpnmt {

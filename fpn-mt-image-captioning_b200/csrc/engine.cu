@@ -55,6 +55,11 @@ Engine::~Engine() {
     if (stage_ready_[i]) cudaEventDestroy(stage_ready_[i]);
     if (stage_free_[i]) cudaEventDestroy(stage_free_[i]);
   }
+  if (lane_dec_stream_) {
+    cudaStreamSynchronize(lane_dec_stream_);
+    cudaStreamDestroy(lane_dec_stream_);
+  }
+  if (lane_enc_ev_) cudaEventDestroy(lane_enc_ev_);
   if (lane_stream_) {
     cudaStreamSynchronize(lane_stream_);
     cudaStreamDestroy(lane_stream_);
@@ -1765,26 +1770,42 @@ int Engine::generate_staged(int slot, int32_t* out_ids, int32_t* out_len, int ou
 // must stay valid until collect).  A fixed-length decode is enqueued completely at submit; an early-stop decode needs the host
 // to look at the finished-image counter, so submit enqueues the encoder only and collect drives the decode - the encoder of the
 // batch submitted on another lane in between still overlaps it.
-int Engine::submit(const float* images, int on_host, int early_stop, cudaStream_t caller) {
+int Engine::submit(const float* images, int on_host, int early_stop, cudaStream_t caller, cudaEvent_t prev_encode_done) {
   if (!finalized_) return fail(FPNMT_ERR_STATE, "submit before finalize_weights");
   if (lane_state_ != 0) return fail(FPNMT_ERR_STATE, "submit: this lane still holds a batch (call fpnmt_collect first)");
   if (!images) return fail(FPNMT_ERR_INVALID, "images is NULL");
   FPNMT_CUDA_OK(cudaSetDevice(dev_));
   if (!lane_stream_) {
+    // Two streams per lane, encoder and decode chain, at EQUAL priority.  Measured on C2 with 4 lanes: decode streams at the
+    // highest priority starve the encoder at every one of its 151 kernel boundaries (2 950 -> 1 960 images/s with the encoder
+    // chain below, 2 650 without it); encoder-high is neutral (2 920).
     FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&lane_stream_, cudaStreamNonBlocking));
+    FPNMT_CUDA_OK(cudaStreamCreateWithFlags(&lane_dec_stream_, cudaStreamNonBlocking));
     FPNMT_CUDA_OK(cudaEventCreateWithFlags(&lane_in_ev_, cudaEventDisableTiming));
     FPNMT_CUDA_OK(cudaEventCreateWithFlags(&lane_out_ev_, cudaEventDisableTiming));
+    FPNMT_CUDA_OK(cudaEventCreateWithFlags(&lane_enc_ev_, cudaEventDisableTiming));
   }
+  FPNMT_CUDA_OK(cudaStreamWaitEvent(lane_stream_, lane_out_ev_, 0));   // the previous batch of this lane has left the decode stream
   if (!on_host) {
     FPNMT_CUDA_OK(cudaEventRecord(lane_in_ev_, caller));
     FPNMT_CUDA_OK(cudaStreamWaitEvent(lane_stream_, lane_in_ev_, 0));
   }
-  RC(encode(images, on_host, nullptr, lane_stream_, false));
+  RC(set_images(images, on_host, lane_stream_));
+  // Encoders of different lanes run one after the other, in submission order: they are throughput-bound (nothing is gained by
+  // running two at once) and a staggered pipeline - one encoder under the decodes of the other lanes - is what the lanes are
+  // for.  Without the chain the overlap depends on when the host happens to submit (measured: 2 920 -> 2 960 images/s, and
+  // the run-to-run spread of the device-resident figure shrinks).
+  if (prev_encode_done) FPNMT_CUDA_OK(cudaStreamWaitEvent(lane_stream_, prev_encode_done, 0));
+  if (cfg_.use_graphs && !enc_graph_) RC(capture(enc_prog_, &enc_graph_));
+  RC(launch_prog(enc_prog_, enc_graph_, lane_stream_));
+  FPNMT_CUDA_OK(cudaEventRecord(lane_enc_ev_, lane_stream_));
+  FPNMT_CUDA_OK(cudaStreamWaitEvent(lane_dec_stream_, lane_enc_ev_, 0));
   if (early_stop) {
     lane_state_ = 2;
     return 0;
   }
-  RC(decode(nullptr, nullptr, 0, 0, nullptr, lane_stream_));
+  RC(decode(nullptr, nullptr, 0, 0, nullptr, lane_dec_stream_));
+  FPNMT_CUDA_OK(cudaEventRecord(lane_out_ev_, lane_dec_stream_));
   lane_state_ = 1;
   return 0;
 }
@@ -1796,16 +1817,16 @@ int Engine::collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_
   const int st = lane_state_;
   lane_state_ = 0;
   if (st == 2) {
-    RC(decode(out_ids, out_len, on_host, 1, nullptr, lane_stream_));
+    RC(decode(out_ids, out_len, on_host, 1, nullptr, lane_dec_stream_));
   } else {
     const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (out_ids) FPNMT_CUDA_OK(cudaMemcpyAsync(out_ids, bs_.out_ids, (size_t)B * T * 4, kind, lane_stream_));
-    if (out_len) FPNMT_CUDA_OK(cudaMemcpyAsync(out_len, bs_.out_len, (size_t)B * 4, kind, lane_stream_));
+    if (out_ids) FPNMT_CUDA_OK(cudaMemcpyAsync(out_ids, bs_.out_ids, (size_t)B * T * 4, kind, lane_dec_stream_));
+    if (out_len) FPNMT_CUDA_OK(cudaMemcpyAsync(out_len, bs_.out_len, (size_t)B * 4, kind, lane_dec_stream_));
   }
+  FPNMT_CUDA_OK(cudaEventRecord(lane_out_ev_, lane_dec_stream_));
   if (on_host) {
-    FPNMT_CUDA_OK(cudaStreamSynchronize(lane_stream_));
+    FPNMT_CUDA_OK(cudaStreamSynchronize(lane_dec_stream_));
   } else {
-    FPNMT_CUDA_OK(cudaEventRecord(lane_out_ev_, lane_stream_));
     FPNMT_CUDA_OK(cudaStreamWaitEvent(caller, lane_out_ev_, 0));
   }
   return 0;

@@ -77,15 +77,16 @@ class Engine {
                       cudaStream_t s);
   // Lane interface (fpnmt_submit / fpnmt_collect): one batch in flight per engine on the engine's own stream, so that several
   // engines ("lanes") of one handle overlap the throughput-bound encode of one batch with the latency-bound decode of another.
-  int submit(const float* images, int on_host, int early_stop, cudaStream_t caller);
+  int submit(const float* images, int on_host, int early_stop, cudaStream_t caller, cudaEvent_t prev_encode_done = nullptr);
+  cudaEvent_t encode_done_event() const { return lane_enc_ev_; }   // recorded after the encoder of the last submitted batch
   int collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_t caller);
   const fpnmt_config& config() const { return cfg_; }
   int device() const { return dev_; }
   int64_t launches = 0;
 
  private:
-  cudaStream_t lane_stream_ = nullptr;
-  cudaEvent_t lane_in_ev_ = nullptr, lane_out_ev_ = nullptr;
+  cudaStream_t lane_stream_ = nullptr, lane_dec_stream_ = nullptr;   // encoder / decode chain of the lane's batch
+  cudaEvent_t lane_in_ev_ = nullptr, lane_out_ev_ = nullptr, lane_enc_ev_ = nullptr;
   int lane_state_ = 0;                    // 0 idle, 1 = fixed-length batch enqueued, 2 = encode enqueued, early-stop decode runs in collect()
   fpnmt_config cfg_;
   int dev_;
