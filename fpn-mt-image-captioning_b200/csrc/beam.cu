@@ -37,6 +37,7 @@ __global__ void k_beam_init(BeamState st, int true_beam) {
     if (st.finished_mode) st.fin_len[0][i] = 0;
     st.seq[0][(size_t)i * (st.T + 1)] = st.start_id;
     st.last_tok[i] = st.start_id;
+    if (st.rep[0]) st.rep[0][i] = i - n;                   // every beam starts from <start>: one history per image
   }
   for (size_t j = i; j < (size_t)st.B * st.T; j += (size_t)gridDim.x * blockDim.x) st.out_ids[j] = 0;
 }
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   __shared__ float s_m[NW], s_s[NW];
   __shared__ float s_cv[NW * 32];
   __shared__ int s_ci[NW * 32];
-  __shared__ int s_parent[32], s_token[32];
+  __shared__ int s_parent[32], s_token[32], s_rep[32];
   __shared__ int s_last;
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -383,16 +384,33 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
   }
   __syncthreads();
   BDBG(9);
+  // representative of each new beam: the first new beam with the same token history (parents equivalent, same token)
+  if (tid < N) {
+    int m_sel = tid;
+    if (st.rep[0]) {
+      const int* rc = st.rep[cur] + rows0;
+      const int rn = rc[s_parent[tid]], tk = s_token[tid];
+      for (int m = 0; m < tid; ++m)
+        if (s_token[m] == tk && rc[s_parent[m]] == rn) {
+          m_sel = m;
+          break;
+        }
+      st.rep[nxt][rows0 + tid] = rows0 + m_sel;
+    }
+    s_rep[tid] = m_sel;
+  }
+  __syncthreads();
   for (int n = warp; n < N; n += NW) {
     const int par = s_parent[n], tok = s_token[n];
     const int* sseq = st.seq[cur] + (size_t)(rows0 + par) * (T + 1);
     int* dseq = st.seq[nxt] + (size_t)(rows0 + n) * (T + 1);
     for (int j = lane; j <= t; j += 32) dseq[j] = sseq[j];            // pipeline.py:134-137
     if (!st.physical) {                                               // ancestry cache mode: move the indirection, not the cache
-      const int* sanc = st.anc[cur] + (size_t)(rows0 + par) * T;
+      const int apar = s_parent[s_rep[n]];                            // the representative's lineage: identical K/V bits
+      const int* sanc = st.anc[cur] + (size_t)(rows0 + apar) * T;
       int* danc = st.anc[nxt] + (size_t)(rows0 + n) * T;
       for (int j = lane; j < t; j += 32) danc[j] = sanc[j];
-      if (lane == 0) danc[t] = rows0 + par;
+      if (lane == 0) danc[t] = rows0 + apar;
     }
     if (lane == 0) dseq[t + 1] = tok;
   }

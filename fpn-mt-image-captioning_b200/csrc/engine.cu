@@ -877,6 +877,11 @@ int Engine::build_decoder() {
   bs_.anc[0] = anc;
   bs_.anc[1] = anc + (size_t)R * T;
   bs_.last_tok = (int*)dalloc((size_t)R * 4);
+  {
+    int* rep = (cfg_.kernel_opts & FPNMT_OPT_NO_KV_SHARE) ? nullptr : (int*)dalloc((size_t)2 * R * 4);
+    bs_.rep[0] = rep;
+    bs_.rep[1] = rep ? rep + R : nullptr;
+  }
   bs_.step = (int*)dalloc(16);
   bs_.done = (int*)dalloc((size_t)B * 4);
   bs_.n_done = (int*)dalloc(16);
@@ -1180,6 +1185,7 @@ int Engine::build_decoder() {
           st.score[i] = bs_.score[i] + r0;
           st.seq[i] = bs_.seq[i] + (size_t)r0 * (T + 1);
           st.anc[i] = bs_.anc[i] + (size_t)r0 * T;
+          st.rep[i] = bs_.rep[i] ? bs_.rep[i] + r0 : nullptr;
         }
         st.last_tok = bs_.last_tok + r0;
         st.step = (int*)dalloc(16);

@@ -73,6 +73,12 @@ struct BeamState {
   float* score[2];           // [B*N] double-buffered beam scores
   int* seq[2];               // [B*N][T+1] token sequences (seq[.][0] = <start>)
   int* anc[2];               // [B*N][T] physical cache row per position
+  int* rep[2];               // [B*N] per step parity (may be null): representative row = the first beam of the image with the
+                             // same token history.  Beams with equal histories hold bit-identical K/V (same inputs, same
+                             // instructions), so the beam kernel points a beam's ancestry at its representative's cache rows:
+                             // under the reference's beam initialisation (all beams identical, pipeline.py:101-102) the
+                             // attention kernels then read ONE set of cache lines per image instead of one per beam (8x less
+                             // HBM traffic); every row still computes and appends its own K/V and its own attention.
   int* last_tok;             // [B*N] token fed to the next step
   int* step;                 // device scalar: current step t (0-based)
   int* done;                 // [B] 1 once the image's top beam has emitted <end>

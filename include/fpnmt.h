@@ -57,6 +57,9 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
                                         Default: tgemmw_kernel when fpnmt_config.lanes >= 2, else tgemm_kernel (lowest
                                         latency of a single chain)                                                         */
        FPNMT_OPT_NO_TGEMM_WIDE = 1024, /* never tgemmw_kernel                                                             */
+       FPNMT_OPT_NO_KV_SHARE = 2048, /* ancestry cache mode: every beam reads its own lineage's cache rows even when another
+                                        beam of the image has the same token history (default: read the first such beam's rows;
+                                        identical bits, 8x less cache traffic under the reference's beam initialisation)    */
        FPNMT_OPT_DSTEP_TAPS = 128    /* fused decoder: also keep every layer's LayerNorm outputs (fpnmt_get_tap "decL_outK") */ };
 enum { FPNMT_CACHE_ANCESTRY = 0,     /* KV cache never moves; an ancestry table maps (beam, position) -> physical row    */
        FPNMT_CACHE_PHYSICAL = 1 };   /* KV cache rows are gathered by beam parent after every step (bandwidth kernel)    */

@@ -50,3 +50,23 @@ def test_physical_mode_is_rejected_where_it_cannot_run():
         Engine(w, backbone=BB, batch=2, beam=4, vocab=512, max_len=8, num_layers=L, image_size=S, cache_mode="physical", decode_path="fused")
     with pytest.raises(FpnmtError):
         Engine(w, backbone=BB, batch=4, beam=4, vocab=512, max_len=8, num_layers=L, image_size=S, cache_mode="physical", dec_groups=2)
+
+
+@pytest.mark.parametrize("true_beam,finished", [(False, False), (True, False), (True, True)])
+def test_shared_cache_rows_of_identical_beams_change_nothing(true_beam, finished):
+    """Ancestry mode points a beam at the cache rows of the first beam of its image with the same token history
+    (BeamState::rep); with the sharing switched off (opts no_kv_share) every beam walks its own lineage.  Same bits either way:
+    ids, lengths and per-step scores are identical, under the reference's identical beams and under true beams."""
+    from fpnmt.engine import Engine
+    w = O.caption_weights(BB, vocab=V, layers=L, seed=3, end_bias=6.0)
+    img = O.test_images(B, S, seed=43).cuda()
+    res = []
+    for opts in ((), ("no_kv_share",)):
+        eng = Engine(w, backbone=BB, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
+                     true_beam=true_beam, finished_beams=finished, length_penalty=0.6 if finished else 0.0, decode_path="chain", opts=opts)
+        ids, lens, sc = eng.generate(img, early_stop=False, return_scores=True)
+        ids_es, lens_es = eng.generate(img, early_stop=True)
+        res.append((ids.clone(), lens.clone(), sc.cpu().clone(), ids_es.clone(), lens_es.clone()))
+        eng.close()
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
