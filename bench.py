@@ -308,6 +308,10 @@ def run_own(args, wl):
     fd.barrier()
     ms_e2e_sync = fd.max_over_ranks(e0.elapsed_time(e1), dev)
 
+    # ---- strong-scaling point (N > 1): the SAME global batch of 64 images cut over the N GPUs (64 / N images per rank)
+    strong = None
+    if world > 1 and args.workload == "c2" and not args.no_extra and B % world == 0:
+        strong = strong_scaling_point(wl, B // world, args, dev, local, world, eng_opts, fd)
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -337,7 +341,7 @@ def run_own(args, wl):
             f["flops"] += o["flops"] * mult
             f["bytes"] += o["bytes"] * mult
     names = {"igemm": "igemm_kernel (tcgen05 implicit-GEMM convolutions / encoder projections)",
-             "tgemm": "tgemm_kernel (tcgen05 skinny-row Dense layers of the decode step, LayerNorm fused)",
+             "tgemm": "tgemmw_kernel / tgemm_kernel (tcgen05 Dense layers of the decode step, LayerNorm fused; wide-row kernel when lanes >= 2)",
              "xattn": "xattn_kernel (tcgen05 fused decoder cross-attention block: Q-proj + attention + O-proj + residual + LayerNorm)",
              "dstep": "dstep_kernel (cluster-stationary fused decoder: all layers + vocabulary projection + beam tail of a step, tcgen05)",
              "attention": "attention kernels (mma.sync encoder flash attention; decode self/cross attention)",
@@ -349,7 +353,7 @@ def run_own(args, wl):
     total_us = sum(f["us"] for f in fam.values())
     dom = max(fam, key=lambda k: fam[k]["us"])
     traffic_tables = {}
-    for fn in ("r01_ncu_traffic_igemm_encode.json", "r01_ncu_traffic_decode_step.json"):
+    for fn in ("r02_g_ncu_traffic_igemm_encode.json", "r02_g_ncu_traffic_decode_step.json"):
         pth = os.path.join(ROOT, "profiles", fn)
         if os.path.exists(pth):
             with open(pth) as f:
@@ -369,17 +373,19 @@ def run_own(args, wl):
     roofline = family_entry(dom)
     # measured DRAM traffic per launch of the dominant family (ncu --set full captures summarised under profiles/)
     traffic, traffic_src = None, None
-    if dom == "tgemm" and "r01_ncu_traffic_decode_step.json" in traffic_tables:
-        ks = traffic_tables["r01_ncu_traffic_decode_step.json"]["kernels"]
-        tg = [v for k, v in ks.items() if k.startswith("tgemm_kernel")]
+    fam_kernels = {"tgemm": ("tgemm",), "xattn": ("xattn_kernel",), "attention": ("k_dec_self_attention",), "beam": ("k_beam_step",)}
+    if dom in fam_kernels and "r02_g_ncu_traffic_decode_step.json" in traffic_tables:
+        ks = traffic_tables["r02_g_ncu_traffic_decode_step.json"]["kernels"]
+        tg = [v for k, v in ks.items() if k.startswith(fam_kernels[dom])]
         if tg:
             traffic = sum(v["mean_dram_bytes"] * v["launches"] for v in tg) / sum(v["launches"] for v in tg)
-            traffic_src = ("profiles/r01_ncu_traffic_decode_step.json (ncu --set full, mean over %d tgemm launches, cold cache)"
-                           % sum(v["launches"] for v in tg))
-    elif dom == "igemm" and "r01_ncu_traffic_igemm_encode.json" in traffic_tables and wl["backbone"] == "resnet50":
-        ops_t = traffic_tables["r01_ncu_traffic_igemm_encode.json"]["ops"]
+            traffic_src = ("profiles/r02_g_ncu_traffic_decode_step.json (ncu --set full of one decode step, mean over its %d %s "
+                           "launches, cold cache)" % (sum(v["launches"] for v in tg), dom))
+    elif dom == "igemm" and "r02_g_ncu_traffic_igemm_encode.json" in traffic_tables and wl["backbone"] == "resnet50":
+        ops_t = traffic_tables["r02_g_ncu_traffic_igemm_encode.json"]["ops"]
         traffic = sum(v["dram_bytes"] for v in ops_t.values()) / len(ops_t)
-        traffic_src = "profiles/r01_ncu_traffic_igemm_encode.json (ncu, mean over the 124 igemm launches of one encode)"
+        traffic_src = ("profiles/r02_g_ncu_traffic_igemm_encode.json (ncu, mean over the %d igemm_kernel launches of one encode)"
+                       % len(ops_t))
     roofline["traffic"] = traffic
     roofline["traffic_source"] = traffic_src
     roofline["peak_source"] = peaks["source"] + (", sustained bf16 cuBLAS (kernel timed inside a long step)" if roofline["bound"] == "tensor"
@@ -437,6 +443,12 @@ def run_own(args, wl):
         torch.cuda.synchronize()
         msp = e0.elapsed_time(e1) / kp
         ids_p, _ = engp.generate(dev_imgs[(args.steps - 1) % 2], early_stop=False, to_host=False)   # same batch as ids_check
+        ids_p = ids_p.clone()                      # before the profiler reuses the engine's buffers
+        if not torch.equal(ids_p.cpu(), ids_check.cpu()[:B]):
+            sys.stderr.write("physical vs ancestry ids differ: %s %s vs %s %s; rows differing %s; first rows %s | %s\n" % (
+                tuple(ids_p.shape), ids_p.dtype, tuple(ids_check.shape), ids_check.dtype,
+                int((ids_p.cpu() != ids_check.cpu()[:B]).any(dim=1).sum()) if ids_p.shape == ids_check[:B].shape else "n/a",
+                ids_p[0, :8].tolist(), ids_check[0, :8].tolist()))
         profp = engp.profile(iters=args.profile_iters)
         ko = [o for o in profp["decode_step"] if o["kind"] == "kvreorder"]
         gbs = ko[0]["bytes"] / (ko[0]["us"] * 1e-6) / 1e9 if ko else None
@@ -445,9 +457,13 @@ def run_own(args, wl):
                        "reorder_us_at_t": ko[0]["us"] if ko else None, "t": profp.get("decode_step_t"),
                        "algorithmic_bytes": ko[0]["bytes"] if ko else None, "achieved_gbs": gbs,
                        "frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if gbs else None,
-                       "ids_equal_ancestry_mode": bool(torch.equal(ids_p.cpu(), ids_check.cpu()[:B])) if world == 1 else None,
+                       "ids_equal_ancestry_mode": bool(torch.equal(ids_p.cpu(), ids_check.cpu()[:B])),
                        "note": "the default cache mode (ancestry table) moves 4 bytes per (beam, position) instead"}
         engp.close()
+    eng.close()
+    other = None
+    if world == 1 and args.workload == "c2" and args.precision == "bf16" and not args.no_extra:
+        other = {k: quick_workload(k, 2, dev, eng_opts) for k in ("c3", "c4")}
     cb = None
     if world == 1 and not args.no_cpu:
         cb = cpu_reference_sample(wl, 3, 1)
@@ -475,10 +491,78 @@ def run_own(args, wl):
                          "api": "Engine.generate (one batch, nothing else in flight, device-resident inputs)",
                          "ids_equal_streamed": lanes_equal},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
-            "parity_mode": parity_mode, "kv_cache_physical": kv_physical,
+            "parity_mode": parity_mode, "kv_cache_physical": kv_physical, "other_workloads": other, "strong_scaling": strong,
             "model_tflops": flop_total / (ms * 1e-3) / 1e12,
             "ids_checksum": int(ids_check.to(torch.int64).sum().item())}
     print(json.dumps(line), flush=True)
+
+
+def quick_workload(key, lanes, dev, opts):
+    """Another BASELINE.json config through the same streaming call, device-resident inputs, a short run (driver-visible
+    breadth: value, ms per batch and the kernel family with the largest share of the per-op device time)."""
+    import torch
+    from fpnmt.engine import Engine
+    from fpnmt.weights import init_weights
+    wl = WORKLOADS[key]
+    B, N, V, T = wl["batch"], wl["beam"], wl["vocab"], wl["max_len"]
+    eng = Engine(init_weights(wl["backbone"], vocab=V, seed=0), backbone=wl["backbone"], batch=B, beam=N, vocab=V, max_len=T,
+                 precision="bf16", score_mode="log", device=dev.index or 0, lanes=lanes, opts=opts)
+    g = torch.Generator().manual_seed(99)
+    imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).to(dev) for _ in range(2)]
+
+    def run(n):
+        for _ in eng.generate_stream((imgs[i % 2] for i in range(n)), early_stop=False, to_host=False):
+            pass
+    run(2 * lanes)
+    torch.cuda.synchronize()
+    k = 6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    prof = eng.profile(iters=3)
+    fam = {}
+    for ops, mult in ((prof["encode"], 1), (prof["decode_step"], T)):
+        for o in ops:
+            fam[o["kind"]] = fam.get(o["kind"], 0.0) + o["us"] * mult
+    eng.close()
+    del imgs
+    torch.cuda.empty_cache()
+    dom = max(fam, key=fam.get)
+    return {"workload": wl["name"], "value": B / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "steps": k, "lanes": lanes,
+            "dominant_family": dom, "dominant_share_of_device_time": fam[dom] / sum(fam.values())}
+
+
+def strong_scaling_point(wl, b_local, args, dev, local, world, opts, fd):
+    """Global batch fixed at the C2 batch (64 images) and cut over the ranks: exposes the latency-bound decode chain that weak
+    scaling hides.  Same streaming call, device-resident inputs, max over ranks."""
+    import torch
+    from fpnmt.engine import Engine
+    from fpnmt.weights import init_weights
+    N, V, T = wl["beam"], wl["vocab"], wl["max_len"]
+    eng = Engine(init_weights(wl["backbone"], vocab=V, seed=0), backbone=wl["backbone"], batch=b_local, beam=N, vocab=V, max_len=T,
+                 precision="bf16", score_mode="log", device=local, lanes=args.lanes, opts=opts)
+    g = torch.Generator().manual_seed(4321 + local)
+    imgs = [(torch.rand(b_local, 512, 512, 3, generator=g) * 2 - 1).to(dev) for _ in range(2)]
+
+    def run(n):
+        for ids, lens in eng.generate_stream((imgs[i % 2] for i in range(n)), early_stop=False, to_host=False):
+            fd.allgather_captions(ids, lens, world)
+    run(2 * max(1, args.lanes))
+    fd.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    fd.barrier()
+    ms = fd.max_over_ranks(e0.elapsed_time(e1), dev)
+    eng.close()
+    return {"global_batch": b_local * world, "batch_per_gpu": b_local, "value": b_local * world * args.steps / (ms * 1e-3),
+            "unit": "images/s", "ms_per_step": ms / args.steps, "steps": args.steps, "scaling": "strong"}
 
 
 def main():
@@ -490,10 +574,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graphs", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per GPU (1 = one batch at a time)")
+    ap.add_argument("--lanes", type=int, default=8, help="batches in flight per GPU (1 = one batch at a time)")
     ap.add_argument("--opts", default="", help="comma-separated fpnmt kernel_opts names (developer A/B, e.g. tgemm_wide)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 throughput leg (parity_mode key)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / strong-scaling legs (other_workloads, strong_scaling keys)")
     ap.add_argument("--profile-iters", type=int, default=10)
     ap.add_argument("--profile-out", default=None, help="write the engine's per-op profile (JSON) here")
     ap.add_argument("--ncu-step", action="store_true", help="bracket one warm step with cudaProfilerStart/Stop (for ncu launch lists)")

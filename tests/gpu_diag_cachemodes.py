@@ -10,9 +10,10 @@ B, N, V, T = 64, 8, 10000, 64
 w = init_weights(bb, vocab=V, seed=0)
 g = torch.Generator().manual_seed(1234)
 imgs = [(torch.rand(B, 512, 512, 3, generator=g) * 2 - 1).cuda() for _ in range(2)]
-kw = dict(backbone=bb, batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log")
+OPTS = tuple(o for o in os.environ.get("DIAG_OPTS", "").split(",") if o)
+kw = dict(backbone=bb, batch=B, beam=N, vocab=V, max_len=T, precision="bf16", score_mode="log", opts=OPTS)
 a = Engine(w, **kw)
-a2 = Engine(w, **kw)
+a2 = Engine(w, **dict(kw, opts=OPTS + ("no_kv_share",)))
 p = Engine(w, cache_mode="physical", **kw)
 for i in range(2):
     ia, la = a.generate(imgs[i], early_stop=False, to_host=True)
