@@ -102,6 +102,83 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) k_beam_step(B
       st.cand_val[(size_t)row * N + tid] = tid == 0 ? score : -INFINITY;
       st.cand_idx[(size_t)row * N + tid] = tid == 0 ? st.end_id : 0x7fffffff;
     }
+  } else if (st.vs_stat) {
+    // ---- phase 1 without logits: merge the per-tile softmax partials and candidates left by the vocabulary projection
+    const int nt = st.vs_tiles, nc = nt * 8;
+    float* s_lv2 = reinterpret_cast<float*>(s_row4);        // [nc] candidate scores that reach the threshold
+    int* s_li2 = reinterpret_cast<int*>(s_lv2 + nc);        // [nc] their token ids
+    __shared__ float s_tau;
+    __shared__ int s_cnt2;
+    const float2* stt = st.vs_stat + (size_t)row * nt;
+    const float* cvv = st.vs_val + (size_t)row * nc;
+    const int* cii = st.vs_idx + (size_t)row * nc;
+    float tm = -INFINITY, ts = 0.f;                          // this thread's tiles: (max, sum relative to it)
+    for (int i = tid; i < nt; i += THREADS) {
+      const float2 q = __ldcg(stt + i);
+      if (q.x > -INFINITY) {
+        const float mn = fmaxf(tm, q.x);
+        ts = ts * __expf(tm - mn) + q.y * __expf(q.x - mn);
+        tm = mn;
+      }
+    }
+    {
+      const float wm = warp_max(tm);
+      const float wsum = warp_sum(tm > -INFINITY ? ts * __expf(tm - wm) : 0.f);
+      if (lane == 0) {
+        s_m[warp] = wm;
+        s_s[warp] = wsum;
+      }
+    }
+    // tile maxima: the N-th largest of them bounds the N-th best logit of the row from below
+    for (int i = tid; i < nt; i += THREADS) s_cv[i] = __ldcg(stt + i).x;
+    if (tid == 0) {
+      s_cnt2 = 0;
+      s_tau = -INFINITY;
+    }
+    __syncthreads();
+    float m = s_m[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, s_m[w]);
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sum += s_m[w] > -INFINITY ? s_s[w] * __expf(s_m[w] - m) : 0.f;
+    const float lse = m + logf(sum);
+    for (int i = tid; i < nt; i += THREADS) {
+      const float g = s_cv[i];
+      int rank = 0;
+      for (int j = 0; j < nt; ++j) {
+        const float gj = s_cv[j];
+        rank += (gj > g || (gj == g && j < i)) ? 1 : 0;
+      }
+      if (rank == N - 1) s_tau = g;                          // ranks are a permutation: exactly one writer (none if nt < N)
+    }
+    __syncthreads();
+    const float tau_raw = s_tau;
+    for (int c = tid; c < nc; c += THREADS) {
+      const int e = __ldcg(cii + c);
+      const float v = __ldcg(cvv + c);
+      if (e != 0x7fffffff && v >= tau_raw) {
+        const int pos = atomicAdd(&s_cnt2, 1);
+        s_lv2[pos] = score + (v - lse);                      // log score mode (the launcher rejects prob mode here)
+        s_li2[pos] = e;
+      }
+    }
+    __syncthreads();
+    const int cnt = s_cnt2;
+    for (int c = tid; c < cnt; c += THREADS) {
+      const float v = s_lv2[c];
+      const int e = s_li2[c];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += better(s_lv2[j], s_li2[j], v, e) ? 1 : 0;
+      if (rank < N) {
+        st.cand_val[(size_t)row * N + rank] = v;
+        st.cand_idx[(size_t)row * N + rank] = e;
+      }
+    }
+    if (cnt < N && tid >= cnt && tid < N) {                  // fewer than N valid tokens (tiny vocabularies): pad
+      st.cand_val[(size_t)row * N + tid] = -INFINITY;
+      st.cand_idx[(size_t)row * N + tid] = 0x7fffffff;
+    }
   } else {
   const int nv4 = (V + 4 * THREADS - 1) / (4 * THREADS);  // float4 slots per thread; slot i of thread tid = elements
   float* s_row = reinterpret_cast<float*>(s_row4);        //   (i*THREADS + tid)*4 .. +3 (conflict-free, coalesced)
@@ -467,6 +544,16 @@ int launch_beam_step(const BeamState& st, const float* logits, int ld, const Bea
   if (st.N > 32 || (ld & 3)) {
     set_last_error("beam_step: beam width must be <= 32 and logits ld a multiple of 4");
     return 1;
+  }
+  if (st.vs_stat) {                                         // logits-free tail: merge the vocabulary projection's candidates
+    if (st.prob_mode || st.N > 8 || st.vs_tiles > 192 || st.vs_tiles < 1) {
+      set_last_error("beam_step: the logits-free tail needs log scores, beam <= 8 and <= 192 vocabulary tiles");
+      return 1;
+    }
+    size_t smem = (size_t)st.vs_tiles * 8 * 8;
+    if (smem < 12288) smem = 12288;
+    FPNMT_CUDA_OK(launch_k_small(k_beam_step<256>, dim3(st.B * st.N), dim3(256), smem, s, st, logits, ld, em));
+    return 0;
   }
   const int threads = st.V <= 16384 ? 256 : 512;
   const int nv4 = (st.V + 4 * threads - 1) / (4 * threads);

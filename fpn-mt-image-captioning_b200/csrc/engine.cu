@@ -1134,9 +1134,39 @@ int Engine::build_decoder() {
         step_forced_prog_ = embed_prog;
         step_forced_prog_.insert(step_forced_prog_.end(), step_prog.begin(), step_prog.end());
       }
+      // Logits-free decode tail (bf16 mode, log scores, beam <= 8, wide Dense kernels): the beam-search chain replaces the
+      // vocabulary projection's [rows][V] fp32 output (20.5 MB written and read back per step at C2) by per-tile softmax
+      // partials + 8 candidates (2.9 MB); teacher forcing (decode_logits) keeps the logits version built above.
+      const int vtiles = (V + TG_BM - 1) / TG_BM;
+      const bool want_wide = (cfg_.kernel_opts & FPNMT_OPT_TGEMM_WIDE) || (cfg_.lanes >= 2 && !(cfg_.kernel_opts & FPNMT_OPT_NO_TGEMM_WIDE));
+      const bool vstats = use_tgemm_ && want_wide && !split_ && !bs.prob_mode && N <= TG_VS_N && vtiles <= 192 && Bg == B &&
+                          !(cfg_.kernel_opts & FPNMT_OPT_NO_VSTATS);
+      BeamState bsv = bs;
+      if (vstats) {
+        float2* vst = (float2*)dalloc((size_t)Rg * vtiles * sizeof(float2));
+        float* vval = (float*)dalloc((size_t)Rg * vtiles * TG_VS_N * sizeof(float));
+        int* vidx = (int*)dalloc((size_t)Rg * vtiles * TG_VS_N * sizeof(int));
+        if (!vst || !vval || !vidx) return FPNMT_ERR_CUDA;
+        TgemmOp op;
+        RC(make_tgemmw_op(&op, Rg, x.a, gf.w, gf.Cout, gf.K, gf.bias, ACT_NONE, none.a, nullptr, 0, nullptr, nullptr, nullptr, 1e-6f,
+                          num_sms_, vst, vval, vidx));
+        op.p.dbg = dbg_timeline("final_layer");
+        Op o;
+        o.name = "final_layer(softmax partials + candidates)" + sfx;
+        o.kind = "tgemm";
+        o.flops = op.flops;
+        o.bytes = (double)Rg * gf.K * 2 + (double)gf.Cout * gf.K * 2 + (double)Rg * vtiles * (8 + 8 * TG_VS_N);
+        o.run = [op](cudaStream_t s) { return tgemm_launch(op, s); };
+        step_prog.back() = std::move(o);                      // replaces the logits version in the beam-search chain
+        bsv.vs_stat = vst;
+        bsv.vs_val = vval;
+        bsv.vs_idx = vidx;
+        bsv.vs_tiles = vtiles;
+      }
       {
-        Op o = ew_op("beam_step" + sfx, [=](cudaStream_t s) { return launch_beam_step(bs, lg, V, em, s); },
-                     (double)Rg * V * 4 + (double)Rg * (T + 1) * 8, "beam");
+        Op o = ew_op("beam_step" + sfx, [=](cudaStream_t s) { return launch_beam_step(bsv, lg, V, em, s); },
+                     vstats ? (double)Rg * vtiles * (8 + 8 * TG_VS_N) + (double)Rg * (T + 1) * 8
+                            : (double)Rg * V * 4 + (double)Rg * (T + 1) * 8, "beam");
         o.idempotent = false;
         step_prog.push_back(std::move(o));
       }

@@ -98,6 +98,13 @@ struct BeamState {
   int finished_mode;
   int* fin_len[2];           // [B*N] per step parity: 0 = live beam, else the length (tokens incl. <end>) at which it finished
   const float* lp;           // [T + 1] length-penalty table
+  // Logits-free decode tail (log score mode, beam <= 8): the vocabulary projection (tgemmw_kernel, TgemmParams::vs_*) leaves
+  // per (row, 128-token tile) softmax partials and its 8 largest logits; phase 1 of k_beam_step merges those instead of
+  // scanning a [rows][V] fp32 logits tensor (which is then never written).  nullptr = the logits path.
+  const float2* vs_stat;     // [B*N][vs_tiles] (max, sum exp(x - max))
+  const float* vs_val;       // [B*N][vs_tiles][8] largest logits of the tile, -inf padded
+  const int* vs_idx;         // [B*N][vs_tiles][8] token ids
+  int vs_tiles;
   int physical;              // 1: "physical" KV-cache mode - the ancestry tables stay the identity (never written here) and
                              // launch_kv_reorder moves the cache rows by beam parent after every step
 };

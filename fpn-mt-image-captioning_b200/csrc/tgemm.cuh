@@ -42,7 +42,13 @@ struct TgemmParams {
   const float* beta;
   float eps;
   long long* dbg;        // optional timeline buffer (globaltimer stamps of block 0), normally nullptr
+  // tgemmw_kernel only - vocabulary projection WITHOUT a logits tensor (decode tail, utils/pipeline.py:115-131): instead of the
+  // [R][F] outputs each (row, 128-feature tile) leaves its softmax partials and its TG_VS_N best logits, which k_beam_step merges.
+  float2* vs_stat;       // [R][ftiles] (max, sum of exp(x - max)) over the tile's valid features, or nullptr = normal outputs
+  float* vs_val;         // [R][ftiles][TG_VS_N] largest logits of the tile, descending, ties -> lower feature first (-inf padded)
+  int* vs_idx;           // [R][ftiles][TG_VS_N] their feature indices (0x7fffffff where padded)
 };
+constexpr int TG_VS_N = 8;   // candidates kept per (row, tile): covers beam widths <= 8
 
 struct TgemmOp {
   CUtensorMap tmW, tmX_hi, tmX_lo;
@@ -69,6 +75,7 @@ int tgemmw_launch(const TgemmOp& op, cudaStream_t stream);
 int tgemmw_set_attributes();
 bool tgemmw_supports(bool split, bool has_res, bool ln, int F, int K);
 int make_tgemmw_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, const float* bias, int act, const Act& out,
-                   float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta, float eps, int num_sms);
+                   float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta, float eps, int num_sms,
+                   float2* vs_stat = nullptr, float* vs_val = nullptr, int* vs_idx = nullptr);
 
 }  // namespace fpnmt

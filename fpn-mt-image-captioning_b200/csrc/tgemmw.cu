@@ -276,7 +276,76 @@ tgemmw_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (warp == 2 && lane == 0 && rt == rt0) DBG(5);
-      if (!is_ln) {
+      if (p.vs_stat) {
+        // ---- vocabulary tile without logits: online (max, sum-exp) and the TG_VS_N largest logits of this row's 128 features,
+        // all in this thread's registers (thread = row).  The list is kept sorted by a compare-exchange chain; scanning the
+        // features in ascending order with strict comparisons gives the tf.math.top_k tie order (lower index first).
+        // (Measured alternative: an unsorted set with a tracked worst slot - 8 selects + a 3-level tree per insertion - is 2.5x
+        // slower, 65 vs 26 us for the C2 projection: the insertion body runs for nearly every element because some lane of the
+        // warp always qualifies, so instruction count matters more than the length of the dependent chain.)
+        float m = -INFINITY, ssum = 0.f;
+        float bv[TG_VS_N];
+        int bi[TG_VS_N];
+#pragma unroll
+        for (int k = 0; k < TG_VS_N; ++k) {
+          bv[k] = -INFINITY;
+          bi[k] = 0x7fffffff;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          float x[32];
+          tw_load_chunk(taddr + ch * 32, sBias + ch * 32, x);
+          if (multi && ch == CHUNKS - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+          }
+          const int fo = f0 + ch * 32;
+          float cm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (fo + i >= p.F) x[i] = -INFINITY;     // padding features of the last tile
+            cm = fmaxf(cm, x[i]);
+          }
+          if (cm > -INFINITY) {
+            const float mn = fmaxf(m, cm);
+            float cs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cs += __expf(x[i] - mn);
+            ssum = ssum * __expf(m - mn) + cs;
+            m = mn;
+          }
+          if (cm > bv[TG_VS_N - 1]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (x[i] > bv[TG_VS_N - 1]) {
+                bv[TG_VS_N - 1] = x[i];
+                bi[TG_VS_N - 1] = fo + i;
+#pragma unroll
+                for (int k = TG_VS_N - 1; k > 0; --k) {
+                  const bool sw = bv[k] > bv[k - 1];
+                  const float tv = sw ? bv[k - 1] : bv[k];
+                  const int ti = sw ? bi[k - 1] : bi[k];
+                  bv[k - 1] = sw ? bv[k] : bv[k - 1];
+                  bi[k - 1] = sw ? bi[k] : bi[k - 1];
+                  bv[k] = tv;
+                  bi[k] = ti;
+                }
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          const size_t slot = (size_t)row * p.ftiles + ftile;
+          p.vs_stat[slot] = make_float2(m, ssum);
+          float4* vo = reinterpret_cast<float4*>(p.vs_val + slot * TG_VS_N);
+          int4* io = reinterpret_cast<int4*>(p.vs_idx + slot * TG_VS_N);
+#pragma unroll
+          for (int k = 0; k < TG_VS_N / 4; ++k) {
+            vo[k] = make_float4(bv[4 * k], bv[4 * k + 1], bv[4 * k + 2], bv[4 * k + 3]);
+            io[k] = make_int4(bi[4 * k], bi[4 * k + 1], bi[4 * k + 2], bi[4 * k + 3]);
+          }
+        }
+      } else if (!is_ln) {
 #pragma unroll 1
         for (int ch = 0; ch < CHUNKS; ++ch) {
           float x[32];
@@ -464,7 +533,8 @@ bool tgemmw_supports(bool split, bool has_res, bool ln, int F, int K) {
 }
 
 int make_tgemmw_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int K, const float* bias, int act, const Act& out,
-                   float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta, float eps, int num_sms) {
+                   float* out_f32, int ld_f32, const Act* res, const float* gamma, const float* beta, float eps, int num_sms,
+                   float2* vs_stat, float* vs_val, int* vs_idx) {
   TgemmParams& p = op->p;
   p = TgemmParams{};
   if (x.C != K) {
@@ -500,6 +570,9 @@ int make_tgemmw_op(TgemmOp* op, int R, const Act& x, const bf16* wt, int F, int 
   p.gamma = gamma;
   p.beta = beta;
   p.eps = eps;
+  p.vs_stat = vs_stat;
+  p.vs_val = vs_val;
+  p.vs_idx = vs_idx;
   op->BN = BN;
   op->wide = 1;
   op->grid = p.ftiles * rgroups;

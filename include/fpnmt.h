@@ -57,6 +57,8 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
                                         Default: tgemmw_kernel when fpnmt_config.lanes >= 2, else tgemm_kernel (lowest
                                         latency of a single chain)                                                         */
        FPNMT_OPT_NO_TGEMM_WIDE = 1024, /* never tgemmw_kernel                                                             */
+       FPNMT_OPT_NO_VSTATS = 4096,   /* keep the [rows][V] fp32 logits between the vocabulary projection and k_beam_step (default with
+                                        the wide Dense kernels, log scores and beam <= 8: per-tile softmax partials + 8 candidates)  */
        FPNMT_OPT_NO_KV_SHARE = 2048, /* ancestry cache mode: every beam reads its own lineage's cache rows even when another
                                         beam of the image has the same token history (default: read the first such beam's rows;
                                         identical bits, 8x less cache traffic under the reference's beam initialisation)    */

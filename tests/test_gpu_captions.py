@@ -74,10 +74,10 @@ def _same(ids, lens, ref_ids, ref_lens):
     return (np.asarray(ids) == ref_ids).all(axis=1) & (np.asarray(lens) == ref_lens)
 
 
-def _run(s, prec, true_beam=False):
+def _run(s, prec, true_beam=False, opts=()):
     from fpnmt.engine import Engine
     eng = Engine(s["w"], backbone=BB, batch=BATCH, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision=prec,
-                 true_beam=true_beam, use_graphs=True)
+                 true_beam=true_beam, use_graphs=True, opts=opts)
     e2e_ids, e2e_lens, dec_ids, dec_lens, lp_err, agree, steps = [], [], [], [], 0.0, 0, 0
     for b0 in range(0, NIMG, BATCH):
         img = s["img"][b0:b0 + BATCH].cuda()
@@ -138,3 +138,46 @@ def test_bf16_benchmarked_mode_parity_numbers(subject):
     print("bf16: identity e2e %.3f decoder-only %.3f, log-prob err %.3f, per-step agreement %.4f" % (same_e2e, same_dec, r["lp_err"], r["agree"]))
     assert r["agree"] >= 0.95 and r["lp_err"] < 1.0, (r["agree"], r["lp_err"])
     assert same_dec >= 0.5, same_dec
+
+
+def test_bf16_lanes_kernel_configuration_parity_numbers(subject):
+    """The kernel set the bench's streamed figure runs on (fpnmt_config.lanes >= 2; forced here with opts tgemm_wide): wide-row
+    Dense kernels (tgemmw_kernel), logits-free decode tail (softmax partials + 8 candidates per vocabulary tile merged by
+    k_beam_step) and shared cache rows.  Same stated tolerance as the lanes = 1 configuration; both beam initialisations."""
+    s = subject
+    r = _run(s, "bf16", opts=("tgemm_wide",))
+    same_e2e = _same(*r["e2e"], s["ids"], s["lens"]).mean()
+    same_dec = _same(*r["dec"], s["ids"], s["lens"]).mean()
+    rt = _run(s, "bf16", true_beam=True, opts=("tgemm_wide",))
+    same_tb = _same(*rt["e2e"], s["ids_tb"], s["lens_tb"]).mean()
+    _record("bf16_lanes_configuration", dict(images=NIMG, sequence_identity_e2e=float(same_e2e), sequence_identity_decoder_only=float(same_dec),
+                                             teacher_forced_logprob_max_abs_err=r["lp_err"], per_step_argmax_agreement=r["agree"],
+                                             true_beam_sequence_identity_e2e=float(same_tb)))
+    print("bf16 (lanes configuration): identity e2e %.3f decoder-only %.3f true-beam e2e %.3f, log-prob err %.3f, per-step agreement %.4f"
+          % (same_e2e, same_dec, same_tb, r["lp_err"], r["agree"]))
+    assert r["agree"] >= 0.95 and r["lp_err"] < 1.0, (r["agree"], r["lp_err"])
+    assert same_dec >= 0.5, same_dec
+
+
+@pytest.mark.parametrize("true_beam,finished", [(False, False), (True, False), (True, True)])
+def test_logits_free_tail_equals_logits_tail(subject, true_beam, finished):
+    """Vocabulary projection + beam step with and without the [rows][V] logits tensor (opts no_vstats): the candidates are the
+    same tokens; scores differ only by the summation order of the softmax denominator (per-tile partial sums), so token ids,
+    lengths and parents must agree and the per-step scores to 1e-4."""
+    from fpnmt.engine import Engine
+    s = subject
+    res = []
+    for opts in (("tgemm_wide",), ("tgemm_wide", "no_vstats")):
+        eng = Engine(s["w"], backbone=BB, batch=BATCH, beam=N, vocab=V, max_len=T, num_layers=L, image_size=S, precision="bf16",
+                     true_beam=true_beam, finished_beams=finished, length_penalty=0.6 if finished else 0.0, opts=opts)
+        ids, lens, sc = eng.generate(s["img"][:BATCH].cuda(), early_stop=False, return_scores=True)
+        ids_es, lens_es = eng.generate(s["img"][:BATCH].cuda(), early_stop=True)
+        res.append((ids.clone(), lens.clone(), sc.cpu().clone(), ids_es.clone(), lens_es.clone()))
+        eng.close()
+    a, b = res
+    same = (a[0] == b[0]).all(dim=1)
+    assert same.float().mean() >= 0.95, same          # a flipped near-tie (scores within rounding) may move a caption
+    assert torch.equal(a[1][same], b[1][same])
+    fin = torch.isfinite(a[2]) & torch.isfinite(b[2])
+    assert float((a[2][fin] - b[2][fin]).abs().max()) < 5e-2
+    assert (a[3] == b[3]).all(dim=1).float().mean() >= 0.95
