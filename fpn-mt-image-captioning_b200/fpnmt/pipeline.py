@@ -77,19 +77,21 @@ class Pipeline:
         ids, lens = self.predict_batch(img[None], max_seq_len)
         return ids[0, :lens[0]], None
 
-    def evaluate(self, generator: Iterable, max_seq_len, batch_size: int = 1) -> List[dict]:
-        """pipeline.py:156-175: [(img, imgId)] -> [{"image_id", "caption"}] (optionally batched)."""
-        # Batches are packed into two alternating pinned buffers and streamed through Engine.generate_stream, so the
+    def evaluate(self, generator: Iterable, max_seq_len, batch_size: int = 1, lanes: int = 1) -> List[dict]:
+        """pipeline.py:156-175: [(img, imgId)] -> [{"image_id", "caption"}] (optionally batched; lanes >= 2 keeps that many
+        batches in flight on the GPU: encoder of batch i+1 under the decode of batch i)."""
+        # Batches are packed into alternating pinned buffers and streamed through Engine.generate_stream, so the
         # host->device copy of batch i+1 overlaps the compute of batch i (dataset.py:90-92's prefetch).
-        eng = self.transformer.engine(int(batch_size), self.beam, max_seq_len or self.max_seq_len)
+        eng = self.transformer.engine(int(batch_size), self.beam, max_seq_len or self.max_seq_len, lanes)
         s = eng.image_size
-        pinned = [None, None]
+        nbuf = max(2, lanes + 1)                                 # a buffer is reused only after its batch was submitted AND copied
+        pinned = [None] * nbuf
         metas: List[list] = []
 
         def pack(buf, k):
-            if pinned[k & 1] is None:
-                pinned[k & 1] = torch.empty((batch_size, s, s, 3), dtype=torch.float32).pin_memory()
-            dst = pinned[k & 1]
+            if pinned[k % nbuf] is None:
+                pinned[k % nbuf] = torch.empty((batch_size, s, s, 3), dtype=torch.float32).pin_memory()
+            dst = pinned[k % nbuf]
             for j, (img, _) in enumerate(buf):
                 dst[j].copy_(torch.as_tensor(img))
             for j in range(len(buf), batch_size):                # pad the last batch

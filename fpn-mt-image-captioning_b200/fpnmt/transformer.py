@@ -57,13 +57,13 @@ class _EngineCache:
                        precision=precision, score_mode=score_mode, device=device, start_id=start_id, end_id=end_id,
                        use_graphs=use_graphs)
         self.max_seq_len = max_seq_len
-        self._engines: Dict[Tuple[int, int, int], Engine] = {}
+        self._engines: Dict[Tuple[int, int, int, int], Engine] = {}
 
-    def get(self, batch: int, beam: int, max_len: Optional[int] = None) -> Engine:
-        key = (batch, beam, max_len or self.max_seq_len)
+    def get(self, batch: int, beam: int, max_len: Optional[int] = None, lanes: int = 1) -> Engine:
+        key = (batch, beam, max_len or self.max_seq_len, max(1, lanes))
         if key not in self._engines:
             self._engines[key] = Engine(self.weights, backbone=self.backbone, batch=batch, beam=beam, max_len=key[2],
-                                        image_size=C.IMAGE_INPUT_SIZE, **self.kw)
+                                        image_size=C.IMAGE_INPUT_SIZE, lanes=key[3], **self.kw)
         return self._engines[key]
 
 
@@ -142,8 +142,9 @@ class Transformer:
 
     call = __call__
 
-    def engine(self, batch: int, beam: int, max_len: Optional[int] = None) -> Engine:
-        return self._cache.get(batch, beam, max_len)
+    def engine(self, batch: int, beam: int, max_len: Optional[int] = None, lanes: int = 1) -> Engine:
+        """The engine for a batch shape; lanes >= 2 = that many batches in flight in `Engine.generate_stream` (throughput)."""
+        return self._cache.get(batch, beam, max_len, lanes)
 
     @property
     def trainable_variables(self):

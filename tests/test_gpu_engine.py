@@ -199,6 +199,11 @@ def test_pipeline_mirror_end_to_end(tmp_path):
     assert res[0]["caption"] == pipe.tokenizer.sequences_to_texts([ids])[0]
     res2 = pipe.evaluate([(img, 17), (img, 18), (img, 19)], 10, batch_size=2)
     assert [r["image_id"] for r in res2] == [17, 18, 19] and all(r["caption"] == res[0]["caption"] for r in res2)
+    # the same through three lanes (batches in flight on the GPU): same rows, same order
+    imgs7 = [(O.test_images(1, 512, seed=20 + i)[0].numpy(), 100 + i) for i in range(7)]
+    rows3 = pipe.evaluate(imgs7, 10, batch_size=2, lanes=3)
+    assert [r["image_id"] for r in rows3] == [100 + i for i in range(7)]
+    assert rows3 == pipe.evaluate(imgs7, 10, batch_size=2, lanes=2)        # (lanes >= 2 share one kernel set)
     # Transformer.call parity surface: logits for a teacher-forced prefix
     mem = pipe.transformer.encoder(torch.from_numpy(img)[None], False, None)
     logits, _ = pipe.transformer(mem, torch.tensor([[2, 5, 9]]), False, None)
