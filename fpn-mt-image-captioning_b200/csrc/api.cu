@@ -57,10 +57,11 @@ FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** o
     int rc = e ? e->init() : FPNMT_ERR_INVALID;
     if (rc) {
       delete e;
-      for (Engine* p : h->lanes) delete p;
+      for (size_t i = h->lanes.size(); i-- > 0;) delete h->lanes[i];
       delete h;
       return rc;
     }
+    if (!h->lanes.empty()) e->share_weights_of(h->lanes[0]);   // one device copy of the GEMM weights for all lanes
     h->lanes.push_back(e);
   }
   h->eng = h->lanes[0];
@@ -70,7 +71,7 @@ FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** o
 
 FPNMT_API int fpnmt_destroy(fpnmt_handle* h) {
   if (!h) return FPNMT_OK;
-  for (Engine* p : h->lanes) delete p;
+  for (size_t i = h->lanes.size(); i-- > 0;) delete h->lanes[i];   // the lead lane (owner of the shared weights) last
   delete h;
   return FPNMT_OK;
 }

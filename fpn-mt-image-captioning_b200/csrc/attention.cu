@@ -318,9 +318,10 @@ __global__ void __launch_bounds__(EA_WARPS * 32) k_enc_attention_mma(Act q, EncA
 }
 
 // Function attributes are per device: called from Engine::init for every device an engine is created on.
+int dec_attention_set_attributes();   // defined next to k_dec_self_attention_mma below
 int attention_set_attributes() {
   FPNMT_CUDA_OK(cudaFuncSetAttribute(k_enc_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
-  return 0;
+  return dec_attention_set_attributes();
 }
 
 int launch_enc_attention(Act q, int q_col, Act kv, int k_col, int v_col, int B, int Tq, int Tk, int heads, Act out,
@@ -599,14 +600,19 @@ struct __align__(128) DecAttTile {
   uint4 v[32 * 8];
 };
 
-__global__ void __launch_bounds__(DEC_WARPS * 32, 7) k_dec_self_attention_mma(Act qkv, Act kc0, Act vc0, Act kc1, Act vc1,
+// Launch shape: 8 KB of staging per warp limits an SM to 27 warps with 4-warp CTAs (6 CTAs x (32 + 1) KB), i.e. 3 552 resident
+// warps for the 4 096 (row, head) pairs of C2 - ncu: 1.15 waves, the second one nearly empty and as long as the first.  With
+// 14 warps per CTA two CTAs fit an SM (2 x 113 KB): 28 warps per SM, 293 CTAs <= 296 slots, ONE wave.
+constexpr int DEC_MMA_WARPS = 14;
+__global__ void __launch_bounds__(DEC_MMA_WARPS * 32, 2) k_dec_self_attention_mma(Act qkv, Act kc0, Act vc0, Act kc1, Act vc1,
                                                                               const int* __restrict__ anc_base, size_t anc_stride,
                                                                               const int* __restrict__ step, int rows, int T,
                                                                               int heads, Act out) {
-  __shared__ DecAttTile s_tile[DEC_WARPS];
+  extern __shared__ __align__(128) uint8_t s_tile_raw[];
+  DecAttTile* s_tile = reinterpret_cast<DecAttTile*>(s_tile_raw);
   pdl_launch();
   pdl_wait();
-  const int gw = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+  const int gw = blockIdx.x * DEC_MMA_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = gw / heads, h = gw % heads;
@@ -747,6 +753,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 7) k_dec_self_attention_mma(Ac
   }
 }
 
+int dec_attention_set_attributes() {
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_dec_self_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(DEC_MMA_WARPS * sizeof(DecAttTile))));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(k_dec_self_attention_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return 0;
+}
+
 int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act vcache2, const int* anc, size_t anc_stride,
                               const int* step, int rows, int T, int heads, Act out, cudaStream_t s) {
   const int warps = rows * heads;
@@ -757,7 +770,8 @@ int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act 
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<false>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
                            qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
   else
-    FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention_mma, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
+    FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention_mma, dim3((warps + DEC_MMA_WARPS - 1) / DEC_MMA_WARPS), dim3(DEC_MMA_WARPS * 32),
+                                 DEC_MMA_WARPS * sizeof(DecAttTile), s,
                            qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
   return 0;
 }

@@ -197,6 +197,13 @@ static inline float bf2f(uint16_t h) {
 
 int Engine::upload_gemm(const std::vector<float>& wt, const std::vector<float>& bias, int Cout, int K, GemmW* out) {
   if (K % 8) return fail(FPNMT_ERR_INVALID, "upload_gemm: K must be a multiple of 8");
+  if (weight_lead_) {                               // follower lane: the lead lane's device copy (see engine.cuh)
+    if (gemm_log_pos_ >= weight_lead_->gemm_log_.size() || weight_lead_->gemm_log_[gemm_log_pos_].Cout != Cout ||
+        weight_lead_->gemm_log_[gemm_log_pos_].K != K || weight_lead_->split_ != split_)
+      return fail(FPNMT_ERR_STATE, "lane weight sharing: finalize sequences of the lanes differ");
+    *out = weight_lead_->gemm_log_[gemm_log_pos_++];
+    return 0;
+  }
   const size_t ldw = split_ ? 2 * (size_t)K : (size_t)K;
   std::vector<uint16_t> h((size_t)Cout * ldw);
   for (int r = 0; r < Cout; ++r)
@@ -214,6 +221,7 @@ int Engine::upload_gemm(const std::vector<float>& wt, const std::vector<float>& 
   RC(upload_f32(b, &out->bias));
   out->Cout = Cout;
   out->K = K;
+  gemm_log_.push_back(*out);
   return 0;
 }
 

@@ -77,6 +77,7 @@ class Engine {
                       cudaStream_t s);
   // Lane interface (fpnmt_submit / fpnmt_collect): one batch in flight per engine on the engine's own stream, so that several
   // engines ("lanes") of one handle overlap the throughput-bound encode of one batch with the latency-bound decode of another.
+  void share_weights_of(const Engine* lead) { weight_lead_ = lead; }   // before finalize(); `lead` must outlive this engine
   int submit(const float* images, int on_host, int early_stop, cudaStream_t caller, cudaEvent_t prev_encode_done = nullptr);
   cudaEvent_t encode_done_event() const { return lane_enc_ev_; }   // recorded after the encoder of the last submitted batch
   int collect(int32_t* out_ids, int32_t* out_len, int on_host, cudaStream_t caller);
@@ -142,6 +143,12 @@ class Engine {
   static Tensor chan_view(const Tensor& t, int c0, int C);
   const HostW* W(const std::string& key);
   int upload_gemm(const std::vector<float>& wt, const std::vector<float>& bias, int Cout, int K, GemmW* out);
+  // Lanes share ONE device copy of the GEMM weights: every lane runs the same finalize sequence on the same host weights, so the
+  // i-th upload of a follower lane is the i-th upload of the lead lane (checked by shape).  Without it 8 lanes cycle 8 x 110 MB
+  // of identical weights through the 126 MB L2 and every weight tile of the latency-bound decode GEMMs comes from DRAM.
+  const Engine* weight_lead_ = nullptr;
+  std::vector<GemmW> gemm_log_;
+  size_t gemm_log_pos_ = 0;
   int prep_conv(const std::string& kernel_key, const std::string& bias_key, const std::string& bn, float eps, GemmW* out,
                 int kpad = 0);
   int prep_dense_cat(const std::vector<std::string>& names, GemmW* out);       // concat along outputs

@@ -31,8 +31,8 @@ def run(n, L, what):
                 engs[i % L].encode(img)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e3
-for what in ("dec",):
-    for L in (1, NL):
+for what in tuple(os.environ.get("DIAG_WHAT", "dec").split(",")):
+    for L in sorted({1, 2, NL // 2, NL}):
         run(4, L, what)
         ms = run(16, L, what)
         print("%s-only, %d lanes: %.2f ms per batch%s" % (what, L, ms, " (%.1f us/step)" % (ms * 1e3 / T) if what == "dec" else ""), flush=True)
