@@ -601,13 +601,24 @@ struct __align__(128) DecAttTile {
 };
 
 // Launch shape: 8 KB of staging per warp limits an SM to 27 warps with 4-warp CTAs (6 CTAs x (32 + 1) KB), i.e. 3 552 resident
-// warps for the 4 096 (row, head) pairs of C2 - ncu: 1.15 waves, the second one nearly empty and as long as the first.  With
-// 14 warps per CTA two CTAs fit an SM (2 x 113 KB): 28 warps per SM, 293 CTAs <= 296 slots, ONE wave.
+// warps for the 4 096 (row, head) pairs of C2 - ncu: 1.15 waves.  With 14 warps per CTA two CTAs fit an SM (2 x 113 KB):
+// 28 warps per SM, 293 CTAs <= 296 slots, one wave.
+//
+// Round 2, token-history classes: beams of an image with the same token history (BeamState::rep; under the reference's beam
+// initialisation ALL beams of an image, pipeline.py:101-102) read the same cache rows - so the warp of the class representative
+// computes the attention of every member at once, flash-attention style with the MEMBERS as the MMA rows:
+//   S[member][pos] = Q[member][:] . K[pos][:]     A = the members' queries (m16: up to 8 members + padding), B = K rows (ldmatrix)
+//   O[member][:]  += P[member][pos] . V[pos][:]    A = P straight from the S accumulator layout (bf16 hi + lo), B = V (ldmatrix.trans)
+// - the instruction count of ONE row serves the whole class (the old layout used 1 of 16 MMA rows and 1 of 8 columns), every
+// member's row is still computed and written, and the warps of the other members only append their K/V and leave.  Warps are
+// ordered beam-major, so with one class per image whole CTAs of non-representatives retire at once.  Without `rep` (teacher
+// forcing, true beams that have diverged) every row is its own class: one member per warp, as before.
 constexpr int DEC_MMA_WARPS = 14;
 __global__ void __launch_bounds__(DEC_MMA_WARPS * 32, 2) k_dec_self_attention_mma(Act qkv, Act kc0, Act vc0, Act kc1, Act vc1,
                                                                               const int* __restrict__ anc_base, size_t anc_stride,
-                                                                              const int* __restrict__ step, int rows, int T,
-                                                                              int heads, Act out) {
+                                                                              const int* __restrict__ step, const int* __restrict__ rep_e,
+                                                                              const int* __restrict__ rep_o, int rows, int T,
+                                                                              int heads, int N, Act out) {
   extern __shared__ __align__(128) uint8_t s_tile_raw[];
   DecAttTile* s_tile = reinterpret_cast<DecAttTile*>(s_tile_raw);
   pdl_launch();
@@ -615,7 +626,10 @@ __global__ void __launch_bounds__(DEC_MMA_WARPS * 32, 2) k_dec_self_attention_mm
   const int gw = blockIdx.x * DEC_MMA_WARPS + (threadIdx.x >> 5);
   if (gw >= rows * heads) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int row = gw / heads, h = gw % heads;
+  const int per_beam = (rows / N) * heads;               // beam-major warp order: gw = n * (B * heads) + b * heads + h
+  const int n_beam = gw / per_beam, bh = gw % per_beam;
+  const int b = bh / heads, h = bh % heads;
+  const int row = b * N + n_beam;
   const int d = heads * DH;
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t sK = smem_u32(s_tile[w].k), sV = smem_u32(s_tile[w].v);
@@ -628,24 +642,43 @@ __global__ void __launch_bounds__(DEC_MMA_WARPS * 32, 2) k_dec_self_attention_mm
     a_e[c] = pos < T ? __ldg(anc_e + pos) : 0;
     a_o[c] = pos < T ? __ldg(anc_o + pos) : 0;
   }
+  // representative rows of this image's beams for both step parities (the parity is known once `step` has arrived)
+  int r_e = b * N + lane, r_o = b * N + lane;
+  if (rep_e && lane < N) {
+    r_e = rep_e[b * N + lane];
+    r_o = rep_o[b * N + lane];
+  }
   const int t = *step;
   const bool second = kc1.p != nullptr && (t & 1);      // physical cache mode: odd steps live in the second buffer pair
   const Act kc = second ? kc1 : kc0, vc = second ? vc1 : vc0;
   const int* anc = (t & 1) ? anc_o : anc_e;
   const int a0 = (t & 1) ? a_o[0] : a_e[0], a1 = (t & 1) ? a_o[1] : a_e[1];
+  const int r_l = (t & 1) ? r_o : r_e;                   // lane l < N: representative row of beam l
+  const int my_rep = __shfl_sync(0xffffffffu, r_l, n_beam);
   const bf16* qrow = qkv.p + (size_t)row * qkv.ld + h * DH;
-  // the query as B fragments (k = dims, n = 0): lanes 0..3 hold column 0, every other column is zero
-  uint32_t qb[8];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    qb[2 * ks] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * lane) : 0u;
-    qb[2 * ks + 1] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * lane) : 0u;
-  }
   const uint32_t knew = *reinterpret_cast<const uint32_t*>(qrow + d + 2 * lane);
   const uint32_t vnew = *reinterpret_cast<const uint32_t*>(qrow + 2 * d + 2 * lane);
-  *reinterpret_cast<uint32_t*>(kc.p + ((size_t)row * T + t) * kc.ld + h * DH + 2 * lane) = knew;     // append to the cache
+  *reinterpret_cast<uint32_t*>(kc.p + ((size_t)row * T + t) * kc.ld + h * DH + 2 * lane) = knew;     // every row appends its own K/V
   *reinterpret_cast<uint32_t*>(vc.p + ((size_t)row * T + t) * vc.ld + h * DH + 2 * lane) = vnew;
-  float m = -INFINITY, l = 0.f;
+  if (my_rep != row) return;                             // a member of another beam's class: that beam's warp computes this row
+  const unsigned members = __ballot_sync(0xffffffffu, lane < N && r_l == row);
+  const int nm = __popc(members);
+  // MMA row g = g-th member of the class (rows >= nm are padding)
+  const int mrow = g < nm ? b * N + (int)__fns(members, 0, g + 1) : row;
+  uint32_t qa[4][4];
+  {
+    const bf16* q0 = qkv.p + (size_t)mrow * qkv.ld + h * DH;
+    const bool ok0 = g < nm;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int c = s4 * 16 + 2 * tq;
+      qa[s4][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+      qa[s4][1] = 0u;
+      qa[s4][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+      qa[s4][3] = 0u;
+    }
+  }
+  float m = -INFINITY, l = 0.f;                          // row g of the class (this thread's quad share)
   float o[8][4];
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
@@ -675,76 +708,80 @@ __global__ void __launch_bounds__(DEC_MMA_WARPS * 32, 2) k_dec_self_attention_mm
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    // ---- scores: lanes with lane % 4 == 0 end up with positions {g, g+8} of each 16-position tile
-    float sc[4];
+    // ---- S = Q K^T for the 32 positions (4 n-tiles of 8)
+    float sa[4][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (mt * 16 < kmax) {
-        const int r = mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+    for (int j = 0; j < 4; ++j) {
+      sa[j][0] = sa[j][1] = sa[j][2] = sa[j][3] = 0.f;
+      if (8 * j < kmax) {
+        const int key = 8 * j + (lane & 7);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t a[4];
-          ldsm_x4(a, sK + (uint32_t)(r * 128 + (((ks * 2 + (lane >> 4)) ^ (r & 7)) << 4)));
-          mma_16816(acc, a, qb[2 * ks], qb[2 * ks + 1]);
+        for (int sp = 0; sp < 2; ++sp) {                 // two k-steps (32 dims) per ldmatrix.x4
+          uint32_t kb[4];
+          const int ch = 4 * sp + (lane >> 3);
+          ldsm_x4(kb, sK + (uint32_t)(key * 128 + ((ch ^ (key & 7)) << 4)));
+          mma_16816(sa[j], qa[2 * sp], kb[0], kb[1]);
+          mma_16816(sa[j], qa[2 * sp + 1], kb[2], kb[3]);
         }
       }
-      sc[2 * mt] = (tq == 0 && mt * 16 + g < kmax) ? acc[0] * 0.125f : -INFINITY;
-      sc[2 * mt + 1] = (tq == 0 && mt * 16 + 8 + g < kmax) ? acc[2] * 0.125f : -INFINITY;
     }
-    float cmax = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    // ---- online softmax of row g (scale 1/sqrt(64)); positions beyond the new one are masked
+    float tm = -INFINITY;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, off));
-    const float mn = fmaxf(m, cmax);
+    for (int j = 0; j < 4; ++j) {
+      const int kk = 8 * j + 2 * tq;
+      sa[j][0] = kk < kmax ? sa[j][0] * 0.125f : -INFINITY;
+      sa[j][1] = kk + 1 < kmax ? sa[j][1] * 0.125f : -INFINITY;
+      tm = fmaxf(tm, fmaxf(sa[j][0], sa[j][1]));
+    }
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+    const float mn = fmaxf(m, tm);
     const float corr = __expf(m - mn);
-    float psum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      sc[i] = __expf(sc[i] - mn);                         // exp(-inf) = 0 for the masked entries
-      psum += sc[i];
-    }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
-    l = l * corr + psum;
     m = mn;
+    float ps = 0.f;
+    uint32_t ah[2][4], al[2][4];                         // P as A fragments (bf16 hi + lo parts): k-step kt = positions 16kt..16kt+15
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p0 = __expf(sa[j][0] - mn), p1 = __expf(sa[j][1] - mn);   // exp(-inf) = 0 for the masked entries
+      ps += p0 + p1;
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+      const float2 hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
+      ah[j >> 1][(j & 1) * 2] = *reinterpret_cast<const uint32_t*>(&hh);      // a0 / a2: row g
+      al[j >> 1][(j & 1) * 2] = *reinterpret_cast<const uint32_t*>(&ll);
+      ah[j >> 1][(j & 1) * 2 + 1] = 0u;                                        // a1 / a3: row g + 8 (padding)
+      al[j >> 1][(j & 1) * 2 + 1] = 0u;
+    }
+    l = l * corr + ps;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       o[nb][0] *= corr;
       o[nb][1] *= corr;
     }
-    // ---- o += p . V: probabilities into row 0 of the A tile (lanes 0..3), split into bf16 hi + lo
+    // ---- O += P V
 #pragma unroll
     for (int kt = 0; kt < 2; ++kt) {
       if (kt * 16 < kmax) {
-        const float x0 = __shfl_sync(0xffffffffu, sc[2 * kt], 8 * tq), x1 = __shfl_sync(0xffffffffu, sc[2 * kt], 8 * tq + 4);
-        const float y0 = __shfl_sync(0xffffffffu, sc[2 * kt + 1], 8 * tq), y1 = __shfl_sync(0xffffffffu, sc[2 * kt + 1], 8 * tq + 4);
-        uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
-        if (lane < 4) {
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(y0, y1);
-          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-          const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(y0 - f1.x, y1 - f1.y);
-          ah[0] = *reinterpret_cast<const uint32_t*>(&h0);
-          ah[2] = *reinterpret_cast<const uint32_t*>(&h1);
-          al[0] = *reinterpret_cast<const uint32_t*>(&l0);
-          al[2] = *reinterpret_cast<const uint32_t*>(&l1);
-        }
         const int r = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
-          uint32_t b[4];
-          ldsm_x4_t(b, sV + (uint32_t)(r * 128 + (((np * 2 + (lane >> 4)) ^ (r & 7)) << 4)));
-          mma_16816(o[2 * np], ah, b[0], b[1]);
-          mma_16816(o[2 * np], al, b[0], b[1]);
-          mma_16816(o[2 * np + 1], ah, b[2], b[3]);
-          mma_16816(o[2 * np + 1], al, b[2], b[3]);
+          uint32_t bq[4];
+          ldsm_x4_t(bq, sV + (uint32_t)(r * 128 + (((np * 2 + (lane >> 4)) ^ (r & 7)) << 4)));
+          mma_16816(o[2 * np], ah[kt], bq[0], bq[1]);
+          mma_16816(o[2 * np], al[kt], bq[0], bq[1]);
+          mma_16816(o[2 * np + 1], ah[kt], bq[2], bq[3]);
+          mma_16816(o[2 * np + 1], al[kt], bq[2], bq[3]);
         }
       }
     }
     __syncwarp();                                        // the tile is restaged by the next chunk
   }
-  if (lane < 4) {                                        // row 0 of the accumulators: dims nb*8 + 2*lane, +1
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (g < nm) {                                          // row g of the accumulators: dims nb*8 + 2*tq, +1 of member g
     const float inv = 1.f / l;
-    bf16* orow = out.p + (size_t)row * out.ld + h * DH + 2 * lane;
+    bf16* orow = out.p + (size_t)mrow * out.ld + h * DH + 2 * tq;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[nb][0] * inv, o[nb][1] * inv);
@@ -761,7 +798,8 @@ int dec_attention_set_attributes() {
 }
 
 int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act vcache2, const int* anc, size_t anc_stride,
-                              const int* step, int rows, int T, int heads, Act out, cudaStream_t s) {
+                              const int* step, int rows, int T, int heads, Act out, cudaStream_t s, const int* rep_e,
+                              const int* rep_o, int N) {
   const int warps = rows * heads;
   if (kcache.lo)
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention<true>, dim3((warps + DEC_WARPS - 1) / DEC_WARPS), dim3(DEC_WARPS * 32), 0, s,
@@ -772,7 +810,8 @@ int launch_dec_self_attention(Act qkv, Act kcache, Act vcache, Act kcache2, Act 
   else
     FPNMT_CUDA_OK(launch_k_small(k_dec_self_attention_mma, dim3((warps + DEC_MMA_WARPS - 1) / DEC_MMA_WARPS), dim3(DEC_MMA_WARPS * 32),
                                  DEC_MMA_WARPS * sizeof(DecAttTile), s,
-                           qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, rows, T, heads, out));
+                           qkv, kcache, vcache, kcache2, vcache2, anc, anc_stride, step, (N >= 1 && N <= 8) ? rep_e : nullptr,
+                           (N >= 1 && N <= 8) ? rep_o : nullptr, rows, T, heads, (N >= 1 && rows % N == 0) ? N : 1, out));
   return 0;
 }
 

@@ -235,14 +235,19 @@ int Engine::prep_conv(const std::string& kernel_key, const std::string& bias_key
   const int K = kh * kw * cin;
   const int Kp = kpad ? kpad : K;
   std::vector<float> scale(cout, 1.f), shift(cout, 0.f);
+  if (k->data.size() != (size_t)K * cout) return fail(FPNMT_ERR_INVALID, kernel_key + ": element count does not match its shape");
+  if (kpad && kpad < K) return fail(FPNMT_ERR_INVALID, kernel_key + ": more taps x channels than the layer takes");
   if (!bias_key.empty()) {
     const HostW* b = W(bias_key);
     if (!b) return FPNMT_ERR_MISSING;
+    if (b->data.size() != (size_t)cout) return fail(FPNMT_ERR_INVALID, bias_key + ": expected " + std::to_string(cout) + " values");
     for (int o = 0; o < cout; ++o) shift[o] = b->data[o];
   }
   if (!bn.empty()) {
     const HostW *g = W(bn + "/gamma"), *be = W(bn + "/beta"), *m = W(bn + "/moving_mean"), *v = W(bn + "/moving_variance");
     if (!g || !be || !m || !v) return FPNMT_ERR_MISSING;
+    if (g->data.size() != (size_t)cout || be->data.size() != (size_t)cout || m->data.size() != (size_t)cout || v->data.size() != (size_t)cout)
+      return fail(FPNMT_ERR_INVALID, bn + ": BatchNorm vectors must have " + std::to_string(cout) + " values (the convolution's filters)");
     for (int o = 0; o < cout; ++o) {
       const float s = g->data[o] / sqrtf(v->data[o] + eps);
       shift[o] = (shift[o] - m->data[o]) * s + be->data[o];
@@ -264,6 +269,8 @@ int Engine::prep_dense_cat(const std::vector<std::string>& names, GemmW* out) {
   for (auto& n : names) {
     const HostW* k = W(n + "/kernel");
     if (!k) return FPNMT_ERR_MISSING;
+    if (k->shape.size() != 2 || k->data.size() != (size_t)(k->shape[0] * k->shape[1]))
+      return fail(FPNMT_ERR_INVALID, n + "/kernel: Dense kernel must be rank 2 (in, out)");
     if (in < 0) in = (int)k->shape[0];
     if ((int)k->shape[0] != in) return fail(FPNMT_ERR_INVALID, "prep_dense_cat: input dims differ");
     tot += (int)k->shape[1];
@@ -274,6 +281,7 @@ int Engine::prep_dense_cat(const std::vector<std::string>& names, GemmW* out) {
     const HostW *k = W(n + "/kernel"), *b = W(n + "/bias");
     if (!b) return FPNMT_ERR_MISSING;
     const int co = (int)k->shape[1];
+    if (b->data.size() != (size_t)co) return fail(FPNMT_ERR_INVALID, n + "/bias: expected " + std::to_string(co) + " values");
     for (int i = 0; i < in; ++i)
       for (int o = 0; o < co; ++o) wt[(size_t)(o0 + o) * in + i] = k->data[(size_t)i * co + o];
     for (int o = 0; o < co; ++o) bias[o0 + o] = b->data[o];
@@ -288,7 +296,10 @@ int Engine::prep_dense_stack(const std::vector<std::string>& names, GemmW* out) 
   for (auto& n : names) {
     const HostW* k = W(n + "/kernel");
     if (!k) return FPNMT_ERR_MISSING;
+    if (k->shape.size() != 2 || k->data.size() != (size_t)(k->shape[0] * k->shape[1]))
+      return fail(FPNMT_ERR_INVALID, n + "/kernel: Dense kernel must be rank 2 (in, out)");
     if (co < 0) co = (int)k->shape[1];
+    if ((int)k->shape[1] != co) return fail(FPNMT_ERR_INVALID, "prep_dense_stack: output dims differ (" + n + ")");
     tot += (int)k->shape[0];
   }
   std::vector<float> wt((size_t)co * tot), bias(co, 0.f);
@@ -296,6 +307,7 @@ int Engine::prep_dense_stack(const std::vector<std::string>& names, GemmW* out) 
   for (auto& n : names) {
     const HostW *k = W(n + "/kernel"), *b = W(n + "/bias");
     if (!b) return FPNMT_ERR_MISSING;
+    if (b->data.size() != (size_t)co) return fail(FPNMT_ERR_INVALID, n + "/bias: expected " + std::to_string(co) + " values");
     const int in = (int)k->shape[0];
     for (int i = 0; i < in; ++i)
       for (int o = 0; o < co; ++o) wt[(size_t)o * tot + i0 + i] = k->data[(size_t)i * co + o];
@@ -339,6 +351,8 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
   ConvGeom g{in.N, in.H, in.W, in.a.C, gw.Cout, kh, kw, pad_t, pad_l};
   if (gw.K < kh * kw * in.a.C) return fail(FPNMT_ERR_INVALID, name + ": weight K smaller than kh*kw*Cin");
+  if (out.a.p && gw.Cout != out.a.C)
+    return fail(FPNMT_ERR_INVALID, name + ": the kernel has " + std::to_string(gw.Cout) + " filters, the layer's output " + std::to_string(out.a.C) + " channels");
   IgemmOp op;
   Act r{nullptr, 0, 0, 0};
   if (res) r = res->a;
@@ -360,6 +374,10 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
 int Engine::add_dense(Program& prog, const std::string& name, const Tensor& in, const GemmW& gw, int act, const Tensor* res,
                       const Tensor& out, float* out_f32, int ld_f32, const float* gamma, const float* beta) {
   if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
+  if (gw.K != in.a.C) return fail(FPNMT_ERR_INVALID, name + ": Dense kernel takes " + std::to_string(gw.K) + " inputs, the layer feeds " + std::to_string(in.a.C));
+  if (out.a.p && gw.Cout != out.a.C)
+    return fail(FPNMT_ERR_INVALID, name + ": Dense kernel has " + std::to_string(gw.Cout) + " outputs, the layer's output " + std::to_string(out.a.C));
+  if (out_f32 && gw.Cout > ld_f32) return fail(FPNMT_ERR_INVALID, name + ": Dense kernel has more outputs than the fp32 output row");
   const int R = (int)in.pixels();
   TgemmOp op;
   const bool want_wide = (cfg_.kernel_opts & FPNMT_OPT_TGEMM_WIDE) || (cfg_.lanes >= 2 && !(cfg_.kernel_opts & FPNMT_OPT_NO_TGEMM_WIDE));
@@ -1093,11 +1111,13 @@ int Engine::build_decoder() {
           const int* ancp = anc + (size_t)r0 * T;
           const size_t anc_stride = (size_t)R * T;
           const int* step = bs.step;
+          const int *rep_e = bs.rep[0], *rep_o = bs.rep[1];
           Op o = ew_op(ln + "_self_attn" + sfx,
                        [=](cudaStream_t s) {
                          // teacher forcing (decode_logits) has no beam step and therefore no reorder: it stays in the first buffer pair
                          const Act none{nullptr, 0, 0, 0};
-                         return launch_dec_self_attention(qa, ka, va, forced_mode_ ? none : ka2, forced_mode_ ? none : va2, ancp, anc_stride, step, Rg, T, H, oa, s);
+                         return launch_dec_self_attention(qa, ka, va, forced_mode_ ? none : ka2, forced_mode_ ? none : va2, ancp, anc_stride, step, Rg, T, H, oa, s,
+                                                          forced_mode_ ? nullptr : rep_e, forced_mode_ ? nullptr : rep_o, N);
                        },
                        (double)Rg * (T / 2) * 2 * D * 2, "attention");
           step_prog.push_back(std::move(o));

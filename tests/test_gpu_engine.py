@@ -340,6 +340,20 @@ def test_engine_error_paths():
     assert "final_layer" in str(ei.value)
     with pytest.raises(FpnmtError):
         Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=64, vocab=V, max_len=T, num_layers=L, image_size=256)
+    # malformed weights are rejected by name instead of being read or written out of bounds
+    FE = "transformer/encoder/feature_extractor/retinanet_model"
+    for key, bad, needle in (
+            (FE + "/P4/bias", np.zeros(255, np.float32), "P4/bias"),                                   # short bias vector
+            (FE + "/P4/kernel", np.zeros((3, 3, 256, 264), np.float32), "P4"),                         # more filters than the layer
+            (FE + "/bn_Conv1/gamma", np.zeros(16, np.float32), "bn_Conv1"),                            # BatchNorm vector too short
+            ("transformer/decoder/dec_layers/0/ffn1/bias", np.zeros(100, np.float32), "ffn1/bias"),
+            ("transformer/decoder/dec_layers/0/mha1/wq/kernel", np.zeros((512, 520), np.float32), "")):  # Dense with extra outputs
+        wb = dict(small_weights(bb, V, L, seed=1))
+        assert key in wb, key
+        wb[key] = bad
+        with pytest.raises(FpnmtError) as ei:
+            Engine(wb, backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=256)
+        assert needle in str(ei.value), (key, str(ei.value))
     with pytest.raises(FpnmtError):
         Engine(small_weights(bb, V, L, seed=1), backbone=bb, batch=B, beam=N, vocab=V, max_len=T, num_layers=L, image_size=300)
 
