@@ -350,6 +350,13 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
                      int pad_l, int act, int res_mode, const Tensor* res, const Tensor& out, float* out_f32, int ld_f32) {
   if (!in.a.p || (!out.a.p && !out_f32)) return FPNMT_ERR_CUDA;
   ConvGeom g{in.N, in.H, in.W, in.a.C, gw.Cout, kh, kw, pad_t, pad_l};
+  // A 1x1 convolution is a GEMM over the pixels: run it in the dense geometry (128 consecutive pixels per tile, plain 2-D
+  // operand boxes) unless the residual is the half-resolution map of an FPN lateral.
+  if (kh == 1 && kw == 1 && pad_t == 0 && pad_l == 0 && res_mode != RES_UP2 && !(cfg_.kernel_opts & FPNMT_OPT_NO_DENSE_1X1)) {
+    g.W = in.N * in.H * in.W;
+    g.N = 1;
+    g.H = 1;
+  }
   if (gw.K < kh * kw * in.a.C) return fail(FPNMT_ERR_INVALID, name + ": weight K smaller than kh*kw*Cin");
   if (out.a.p && gw.Cout != out.a.C)
     return fail(FPNMT_ERR_INVALID, name + ": the kernel has " + std::to_string(gw.Cout) + " filters, the layer's output " + std::to_string(out.a.C) + " channels");
@@ -357,7 +364,8 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   Act r{nullptr, 0, 0, 0};
   if (res) r = res->a;
   // a K-padded weight (stem im2col) is addressed with Cin == K
-  RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_));
+  RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_, 0,
+                   !(cfg_.kernel_opts & FPNMT_OPT_NO_TMA_STORE)));
   op.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;

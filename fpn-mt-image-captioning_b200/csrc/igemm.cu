@@ -242,6 +242,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       __syncwarp();
       // residual prefetch for every unit of this warp (in flight while the tile's MMAs are still running)
       if (p.res_mode != RES_NONE && fast) {
+        if (p.tma_store) {                    // the staging buffers may still be the source of the previous tile's bulk stores
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         for (int j = 0; j < nu; ++j) {
           const int col0 = co_t * BN + (u0 + j) * 32;
 #pragma unroll
@@ -359,6 +363,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[q][i] = fminf(fmaxf(v[q][i], 0.f), 6.f);
           }
+          // ---- bf16 output, bulk tensor store: the pair's 32 rows x 64 channels are staged as 128-byte rows in the
+          // SWIZZLE_128B pattern (thread = row: 16-byte chunk c at c ^ (row & 7), conflict-free) and ONE elected lane hands
+          // them to the TMA unit, which writes whole lines and clips rows / channels outside the tensor.  The LSU version below
+          // issues 8 x 64 B per warp instruction and, measured on C2, does not overlap with the rest of the epilogue: removing
+          // the stores took the encoder from 9.6 to 7.8 ms although the kernels are not near the HBM write limit.
+          if (p.out.p && p.tma_store) {
+            uint8_t* buf = my_stage + j * UNIT_BYTES;          // 4 KB, 1 KB aligned (j is even)
+            // this buffer's previous store (one tile ago) has been read.  (Allowing one group in flight for BN = 256 - two
+            // pairs per warp - is wrong when a warp's second pair lies beyond Cout and is skipped: the one pending group is
+            // then this very buffer's.  The TMA unit reads 4 KB of shared memory in well under a microsecond.)
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (q < nun) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  *reinterpret_cast<uint4*>(buf + lane * 128 + (((q * 4 + c) ^ (lane & 7)) << 4)) = pack8(v[q] + c * 8);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int row0 = quarter * 32;
+              const int x0 = tx * p.tw + row0 % p.tw, y0 = ty * p.th + (row0 / p.tw) % p.th, n0 = tn * p.bn + row0 / (p.tw * p.th);
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmA_lo),
+                           "r"(smem_u32(buf)), "r"(colA), "r"(x0), "r"(y0), "r"(n0)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else
           // ---- bf16 output through the staging buffers, transposed 16-byte stores
           if (p.out.p) {
 #pragma unroll
@@ -462,6 +497,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   }
 
+  if (warp >= 2 && lane == 0 && p.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores performed
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) DBG(8);

@@ -34,6 +34,8 @@ struct IgemmParams {
   int res_mode;                   // ResMode; residual is added before the activation
   Act res;                        // RES_SAME: same pixel grid; RES_UP2: (N, H/2, W/2) nearest-upsampled
   long long* dbg;                 // optional timeline buffer (globaltimer stamps of block 0), normally nullptr
+  int tma_store;                  // 1: bf16 outputs leave through bulk tensor stores (output map in the tmA_lo slot; bf16 mode,
+                                  // BN >= 128): see the epilogue
 };
 
 struct IgemmOp {

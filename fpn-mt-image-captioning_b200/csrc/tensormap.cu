@@ -1,5 +1,6 @@
 // CUtensorMap construction through the driver entry point (no link-time dependency on libcuda).
 #include "tensormap.cuh"
+#include <stdlib.h>
 
 #include <cudaTypedefs.h>
 
@@ -70,10 +71,11 @@ static int np2(int v) {
 }
 
 int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt, bool split, const float* bias, int act,
-                  const Act& out, float* out_f32, int ld_f32, int res_mode, const Act& res, int num_sms, int force_bn) {
+                  const Act& out, float* out_f32, int ld_f32, int res_mode, const Act& res, int num_sms, int force_bn, bool tma_store) {
   IgemmParams& p = op->p;
   p = IgemmParams{};
   p.N = g.N; p.H = g.H; p.W = g.W;
+
   if (g.H == 1 && g.N == 1) {           // dense: rows along W
     p.tw = 128; p.th = 1; p.bn = 1;
   } else {
@@ -134,6 +136,20 @@ int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt,
   if (rc) return rc;
   rc = encode_tmap_act(&op->tmA_lo, split ? in.p + in.lo : in.p, in.C, in.ld, g.W, g.H, g.N, p.tw, p.th, p.bn);
   if (rc) return rc;
+  // Output map for the bulk-tensor-store epilogue (kept in the tmA_lo slot, which bf16 mode does not use): an epilogue warp owns
+  // 32 consecutive rows of the 128-row tile = a (bx, by, bz) sub-box of the (tw, th, bn) pixel box, 64 channels per store.
+  p.tma_store = 0;
+  if (!split && out.p && !out.lo && !out_f32 && bn_sel >= 128 && (g.Cout % 8) == 0 && tma_store) {
+    const int bx = p.tw < 32 ? p.tw : 32;
+    const int by = p.th < 32 / bx ? p.th : 32 / bx;
+    const int bz = 32 / (bx * by);
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)out.ld * 2, (cuuint64_t)g.W * out.ld * 2, (cuuint64_t)g.H * g.W * out.ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)IG_BK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    rc = encode(&op->tmA_lo, out.p, 4, dims, strides, box);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   const uint64_t kw_total = split ? 2 * (uint64_t)ktot : (uint64_t)ktot;
   return encode_tmap_2d(&op->tmB, wt, kw_total, (uint64_t)g.Cout, kw_total, bn_sel);
 }
