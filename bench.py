@@ -369,7 +369,7 @@ def run_own(args, wl):
     total_us = sum(f["us"] for f in fam.values())
     dom = max(fam, key=lambda k: fam[k]["us"])
     traffic_tables = {}
-    for fn in ("r02_g_ncu_traffic_igemm_encode.json", "r02_g_ncu_traffic_decode_step.json"):
+    for fn in ("r02_g_ncu_traffic_igemm_encode.json", "r02_k_ncu_traffic_decode_step.json"):
         pth = os.path.join(ROOT, "profiles", fn)
         if os.path.exists(pth):
             with open(pth) as f:
@@ -390,12 +390,12 @@ def run_own(args, wl):
     # measured DRAM traffic per launch of the dominant family (ncu --set full captures summarised under profiles/)
     traffic, traffic_src = None, None
     fam_kernels = {"tgemm": ("tgemm",), "xattn": ("xattn_kernel",), "attention": ("k_dec_self_attention",), "beam": ("k_beam_step",)}
-    if dom in fam_kernels and "r02_g_ncu_traffic_decode_step.json" in traffic_tables:
-        ks = traffic_tables["r02_g_ncu_traffic_decode_step.json"]["kernels"]
+    if dom in fam_kernels and "r02_k_ncu_traffic_decode_step.json" in traffic_tables:
+        ks = traffic_tables["r02_k_ncu_traffic_decode_step.json"]["kernels"]
         tg = [v for k, v in ks.items() if k.startswith(fam_kernels[dom])]
         if tg:
             traffic = sum(v["mean_dram_bytes"] * v["launches"] for v in tg) / sum(v["launches"] for v in tg)
-            traffic_src = ("profiles/r02_g_ncu_traffic_decode_step.json (ncu --set full of one decode step, mean over its %d %s "
+            traffic_src = ("profiles/r02_k_ncu_traffic_decode_step.json (ncu --set full of one decode step, mean over its %d %s "
                            "launches, cold cache)" % (sum(v["launches"] for v in tg), dom))
     elif dom == "igemm" and "r02_g_ncu_traffic_igemm_encode.json" in traffic_tables and wl["backbone"] == "resnet50":
         ops_t = traffic_tables["r02_g_ncu_traffic_igemm_encode.json"]["ops"]

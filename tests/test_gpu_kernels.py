@@ -85,6 +85,27 @@ def test_igemm_all_tile_widths(force_bn):
     assert float((y.double() - ref).norm() / ref.norm()) < 2e-4
 
 
+def test_igemm_bulk_store_epilogue_many_tiles_per_cta_is_deterministic():
+    """Persistent CTAs reuse their output staging buffers tile after tile while earlier bulk tensor stores may still be reading
+    them.  144 filters in a 256-wide tile leave one epilogue warp with a single channel pair per tile - the case in which letting one
+    bulk group stay in flight restaged a buffer under the TMA unit (found by test_batch_invariance_and_determinism_512).  Many
+    tiles per CTA, result against the fp64 reference and bit-identical across runs; also with a residual (its prefetch lands in
+    the same buffers) and in the 2-D pixel-tile geometry (3x3)."""
+    from fpnmt.engine import conv2d
+    g = torch.Generator().manual_seed(7)
+    for (n, h, w, cin, cout, kk, rm) in ((2, 256, 256, 32, 144, 1, 0), (2, 128, 128, 64, 256, 1, 1), (2, 96, 96, 64, 192, 3, 0)):
+        x = torch.randn(n, h, w, cin, generator=g)
+        k = (torch.randn(kk, kk, cin, cout, generator=g) / np.sqrt(kk * kk * cin)).numpy()
+        b = (torch.randn(cout, generator=g) * 0.5).numpy()
+        res = torch.randn(n, h, w, cout, generator=g) if rm else None
+        kw = dict(bias=b, act=1, pad=(kk // 2, kk // 2), residual=None if res is None else res.cuda(), res_mode=rm, precision="bf16")
+        y0 = conv2d(x.cuda(), k, **kw).cpu()
+        ref = _conv_ref(x, k, b, kk // 2, 1, res, rm)
+        assert float((y0.double() - ref).norm() / ref.norm()) < 2e-2
+        for _ in range(3):
+            assert torch.equal(conv2d(x.cuda(), k, **kw).cpu(), y0)
+
+
 def test_igemm_zero_input_and_linearity():
     from fpnmt.engine import conv2d
     g = torch.Generator().manual_seed(1)
