@@ -365,7 +365,7 @@ int Engine::add_conv(Program& prog, const std::string& name, const Tensor& in, c
   if (res) r = res->a;
   // a K-padded weight (stem im2col) is addressed with Cin == K
   RC(make_igemm_op(&op, g, in.a, gw.w, split_, gw.bias, act, out.a, out_f32, ld_f32, res_mode, r, num_sms_, 0,
-                   !(cfg_.kernel_opts & FPNMT_OPT_NO_TMA_STORE)));
+                   !(cfg_.kernel_opts & FPNMT_OPT_NO_TMA_STORE), !(cfg_.kernel_opts & FPNMT_OPT_NO_B_STATIONARY)));
   op.p.dbg = dbg_timeline(name);
   Op o;
   o.name = name;

@@ -16,14 +16,16 @@ namespace fpnmt {
 constexpr int A_STAGE_BYTES = IG_BM * IG_BK * 2;   // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int UNIT_BYTES = 32 * 64;                // 32 rows x 32 bf16 columns
+constexpr int IG_SMEM_MAX = 227 * 1024;            // opt-in limit per CTA on sm_100
 
 __host__ __device__ constexpr int ig_stages(int BN) { return BN == 256 ? 3 : (BN == 128 ? 5 : (BN == 64 ? 6 : 8)); }
 __host__ __device__ constexpr int ig_b_bytes(int BN) { return BN * IG_BK * 2; }
 __host__ __device__ constexpr int ig_units_per_warp(int BN) { return BN >= 64 ? BN / 64 : 1; }
 
 int igemm_stages(int BN) { return ig_stages(BN); }
-size_t igemm_smem_bytes(int BN) {
-  return (size_t)ig_stages(BN) * (A_STAGE_BYTES + ig_b_bytes(BN)) + (size_t)EPI_WARPS * ig_units_per_warp(BN) * UNIT_BYTES +
+size_t igemm_smem_bytes(int BN, int b_chunks) {
+  const int nb = b_chunks > 0 ? b_chunks : ig_stages(BN);
+  return (size_t)ig_stages(BN) * A_STAGE_BYTES + (size_t)nb * ig_b_bytes(BN) + (size_t)EPI_WARPS * ig_units_per_warp(BN) * UNIT_BYTES +
          (size_t)EPI_WARPS * 32 * 2 * sizeof(long long) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
@@ -66,7 +68,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);                 // [EPI_WARPS][UPW][UNIT_BYTES]
+  const int taps = p.taps_y * p.taps_x;
+  const int kiters = p.nterms * taps * p.kchunks;
+  // Stationary weights (p.b_stat): with one output-channel tile every tile of this CTA multiplies by the same [BN][K] panel; it is
+  // fetched ONCE (before the grid dependency resolves) instead of once per tile, and the ring carries only activation chunks.
+  // res2*_2b (3x3, 64 -> 64 channels): 72 KB of the 216 KB a tile used to pull through TMA - the layer is ingest-bound.
+  const int nB = p.b_stat ? kiters : STAGES;
+  uint8_t* sStage = smem + STAGES * A_STAGE_BYTES + nB * B_STAGE_BYTES;               // [EPI_WARPS][UPW][UNIT_BYTES]
   long long* sOff = reinterpret_cast<long long*>(sStage + EPI_WARPS * UPW * UNIT_BYTES);   // [EPI_WARPS][2][32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOff + EPI_WARPS * 64);
   uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
@@ -74,6 +82,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bstat_bar = bars + 2 * STAGES + 5;  // stationary weight panel resident
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,6 +115,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_WARPS * 32);
     }
+    mbar_init(bstat_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -117,8 +127,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = tiles_m * p.tiles_co;
-  const int taps = p.taps_y * p.taps_x;
-  const int kiters = p.nterms * taps * p.kchunks;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -130,6 +138,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const int npre = kiters < STAGES ? kiters : STAGES;
       {
         const int co_t = blockIdx.x % p.tiles_co;
+        if (p.b_stat) {
+          mbar_expect_tx_pred(bstat_bar, kiters * B_STAGE_BYTES, leader);
+          for (int it = 0; it < kiters; ++it)
+            tma_load_2d_pred(sB + it * B_STAGE_BYTES, &tmB, bstat_bar, (it / p.kchunks) * p.Cin + (it % p.kchunks) * IG_BK, 0, leader);
+          for (int it = 0; it < npre; ++it) mbar_expect_tx_pred(&full_bar[it], A_STAGE_BYTES, leader);
+        } else
         for (int it = 0; it < npre; ++it) {
           const int kc = it % p.kchunks;
           const int t = (it / p.kchunks) % taps;
@@ -160,8 +174,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const int stage = git % STAGES;
               if (git >= npre) {
                 mbar_wait(&empty_bar[stage], ((git / STAGES) & 1) ^ 1);
-                mbar_expect_tx_pred(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES, leader);
-                tma_load_2d_pred(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK, co_t * BN, leader);
+                mbar_expect_tx_pred(&full_bar[stage], p.b_stat ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES, leader);
+                if (!p.b_stat)
+                  tma_load_2d_pred(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], bko + t * p.Cin + kc * IG_BK, co_t * BN, leader);
               }
               tma_load_4d_pred(sA + stage * A_STAGE_BYTES, ma, &full_bar[stage], kc * IG_BK, x0 + dx, y0 + dy, n0, leader);
             }
@@ -177,6 +192,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_stat && (int)blockIdx.x < total_tiles) mbar_wait(bstat_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -186,7 +202,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           tc_fence_after();
           if (it == 0 && leader) DBG(3);
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (p.b_stat ? it : stage) * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {
             // +32 bytes (2 x 16 B units) per UMMA_K = 16 bf16 inside the 128 B swizzle atom
@@ -510,7 +526,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
 template <int BN>
 static int launch_bn(const IgemmOp& op, cudaStream_t stream) {
-  FPNMT_CUDA_OK(launch_k(igemm_kernel<BN>, dim3(op.grid), dim3(IG_THREADS), igemm_smem_bytes(BN), stream, op.tmA_hi,
+  FPNMT_CUDA_OK(launch_k(igemm_kernel<BN>, dim3(op.grid), dim3(IG_THREADS), (size_t)op.smem_bytes, stream, op.tmA_hi,
                          op.tmA_lo, op.tmB, op.p));
   return 0;
 }
@@ -527,10 +543,10 @@ int igemm_launch(const IgemmOp& op, cudaStream_t stream) {
 }
 
 int igemm_set_attributes() {
-  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)igemm_smem_bytes(32)));
-  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)igemm_smem_bytes(64)));
-  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)igemm_smem_bytes(128)));
-  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)igemm_smem_bytes(256)));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_MAX));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_MAX));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_MAX));
+  FPNMT_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_MAX));
   return 0;
 }
 

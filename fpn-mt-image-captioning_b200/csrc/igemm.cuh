@@ -34,6 +34,8 @@ struct IgemmParams {
   int res_mode;                   // ResMode; residual is added before the activation
   Act res;                        // RES_SAME: same pixel grid; RES_UP2: (N, H/2, W/2) nearest-upsampled
   long long* dbg;                 // optional timeline buffer (globaltimer stamps of block 0), normally nullptr
+  int b_stat;                     // 1: the whole weight panel [BN][K] stays in shared memory for every tile of the CTA (one output-
+                                  // channel tile, bf16 mode, panel <= 96 KB): the ring then carries only the activation chunks
   int tma_store;                  // 1: bf16 outputs leave through bulk tensor stores (output map in the tmA_lo slot; bf16 mode,
                                   // BN >= 128): see the epilogue
 };
@@ -42,12 +44,13 @@ struct IgemmOp {
   CUtensorMap tmA_hi, tmA_lo, tmB;
   IgemmParams p;
   int BN;     // 32 / 64 / 128 / 256
+  int smem_bytes;   // dynamic shared memory of the launch
   int grid;
   double flops;   // algorithmic FLOPs (2*MAC, one term) for reporting
 };
 
 int igemm_stages(int BN);
-size_t igemm_smem_bytes(int BN);
+size_t igemm_smem_bytes(int BN, int b_chunks = 0);   // b_chunks > 0: stationary weight panel of that many 64-wide k-chunks
 int igemm_launch(const IgemmOp& op, cudaStream_t stream);
 int igemm_set_attributes();   // cudaFuncSetAttribute for every instantiation (call once per device)
 

@@ -71,7 +71,8 @@ static int np2(int v) {
 }
 
 int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt, bool split, const float* bias, int act,
-                  const Act& out, float* out_f32, int ld_f32, int res_mode, const Act& res, int num_sms, int force_bn, bool tma_store) {
+                  const Act& out, float* out_f32, int ld_f32, int res_mode, const Act& res, int num_sms, int force_bn, bool tma_store,
+                  bool b_stationary) {
   IgemmParams& p = op->p;
   p = IgemmParams{};
   p.N = g.N; p.H = g.H; p.W = g.W;
@@ -149,6 +150,16 @@ int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt,
     rc = encode(&op->tmA_lo, out.p, 4, dims, strides, box);
     if (rc) return rc;
     p.tma_store = 1;
+  }
+  // Stationary weight panel: one output-channel tile, bf16 mode, at least two tiles per CTA, panel <= 96 KB and the launch fits
+  p.b_stat = 0;
+  {
+    const int kit = p.taps_y * p.taps_x * p.kchunks;
+    const size_t need = igemm_smem_bytes(bn_sel, kit);
+    if (!split && p.tiles_co == 1 && total >= 2L * op->grid && (size_t)kit * bn_sel * IG_BK * 2 <= 96 * 1024 && need <= 227 * 1024 &&
+        b_stationary)
+      p.b_stat = 1;
+    op->smem_bytes = (int)(p.b_stat ? need : igemm_smem_bytes(bn_sel));
   }
   const uint64_t kw_total = split ? 2 * (uint64_t)ktot : (uint64_t)ktot;
   return encode_tmap_2d(&op->tmB, wt, kw_total, (uint64_t)g.Cout, kw_total, bn_sel);

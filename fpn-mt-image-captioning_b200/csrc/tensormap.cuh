@@ -17,7 +17,7 @@ struct ConvGeom {
 // `split` selects the BF16X3 three-term product.
 int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt, bool split, const float* bias, int act,
                   const Act& out, float* out_f32, int ld_f32, int res_mode, const Act& res, int num_sms, int force_bn = 0,
-                  bool tma_store = true);
+                  bool tma_store = true, bool b_stationary = true);
 
 int encode_tmap_act(CUtensorMap* m, const bf16* base, int C, int ld, int W, int H, int N, int tw, int th, int bn);
 int encode_tmap_2d(CUtensorMap* m, const bf16* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, int box_outer);

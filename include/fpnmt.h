@@ -59,6 +59,8 @@ enum { FPNMT_OPT_NO_XATTN = 1,       /* separate q2 / cross-attention / o2+LN ke
        FPNMT_OPT_NO_TGEMM_WIDE = 1024, /* never tgemmw_kernel                                                             */
        FPNMT_OPT_NO_DENSE_1X1 = 8192, /* 1x1 convolutions in the 2-D pixel-tile geometry of the other convolutions (default: as a
                                         GEMM over 128 consecutive pixels per tile)                                          */
+       FPNMT_OPT_NO_B_STATIONARY = 32768, /* igemm_kernel streams the weight chunks with every tile (default: a panel <= 96 KB of a
+                                        single output-channel tile stays in shared memory for all tiles of the CTA)            */
        FPNMT_OPT_NO_TMA_STORE = 16384, /* igemm_kernel writes its bf16 outputs with 16-byte LSU stores instead of bulk tensor stores */
        FPNMT_OPT_NO_VSTATS = 4096,   /* keep the [rows][V] fp32 logits between the vocabulary projection and k_beam_step (default with
                                         the wide Dense kernels, log scores and beam <= 8: per-tile softmax partials + 8 candidates)  */
