@@ -16,7 +16,7 @@ namespace fpnmt {
 constexpr int A_STAGE_BYTES = IG_BM * IG_BK * 2;   // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int UNIT_BYTES = 32 * 64;                // 32 rows x 32 bf16 columns
-constexpr int IG_SMEM_MAX = 227 * 1024;            // opt-in limit per CTA on sm_100
+constexpr int IG_SMEM_MAX = 226 * 1024;            // opt-in limit per CTA on sm_100 is 227 KB; 1 KB left for static shared memory (debug builds)
 
 __host__ __device__ constexpr int ig_stages(int BN) { return BN == 256 ? 3 : (BN == 128 ? 5 : (BN == 64 ? 6 : 8)); }
 __host__ __device__ constexpr int ig_b_bytes(int BN) { return BN * IG_BK * 2; }

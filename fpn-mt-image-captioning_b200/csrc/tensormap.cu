@@ -156,7 +156,7 @@ int make_igemm_op(IgemmOp* op, const ConvGeom& g, const Act& in, const bf16* wt,
   {
     const int kit = p.taps_y * p.taps_x * p.kchunks;
     const size_t need = igemm_smem_bytes(bn_sel, kit);
-    if (!split && p.tiles_co == 1 && total >= 2L * op->grid && (size_t)kit * bn_sel * IG_BK * 2 <= 96 * 1024 && need <= 227 * 1024 &&
+    if (!split && p.tiles_co == 1 && total >= 2L * op->grid && (size_t)kit * bn_sel * IG_BK * 2 <= 96 * 1024 && need <= 226 * 1024 &&
         b_stationary)
       p.b_stat = 1;
     op->smem_bytes = (int)(p.b_stat ? need : igemm_smem_bytes(bn_sel));
