@@ -46,8 +46,8 @@ FPNMT_API int fpnmt_create(const fpnmt_config* cfg, int device, fpnmt_handle** o
     set_last_error("fpnmt_create: bad device index");
     return FPNMT_ERR_INVALID;
   }
-  if (cfg->lanes < 0 || cfg->lanes > 8) {
-    set_last_error("fpnmt_create: lanes must be 0..8");
+  if (cfg->lanes < 0 || cfg->lanes > 16) {
+    set_last_error("fpnmt_create: lanes must be 0..16");
     return FPNMT_ERR_INVALID;
   }
   const int L = cfg->lanes < 1 ? 1 : cfg->lanes;
