@@ -103,7 +103,8 @@ typedef struct fpnmt_config {
                             stop the moment the top beam emits <end>, finished lower beams keep decoding)          */
   int32_t dec_groups;    /* DECODE_CHAIN only: cut the batch into this many concurrently decoded chains (0/1 = one) */
   int32_t lanes;         /* batches in flight (fpnmt_submit / fpnmt_collect): the handle holds this many complete engines
-                            (own activations, KV cache, beam state, stream) on the one GPU, 0/1 = one.  Two lanes overlap
+                            (own activations, KV cache, beam state, streams; ONE shared copy of the GEMM weights) on the one GPU, 0/1 = one,
+                            at most 16.  Two lanes overlap
                             the throughput-bound encoder of batch i+1 with the latency-bound decode of batch i.            */
   int32_t reserved[1];
 } fpnmt_config;

@@ -64,4 +64,4 @@ def test_lane_call_order_errors():
     del keep
     eng.close()
     with pytest.raises(FpnmtError):
-        Engine(w, backbone=BB, batch=2, beam=4, vocab=512, max_len=8, num_layers=L, image_size=S, lanes=9)
+        Engine(w, backbone=BB, batch=2, beam=4, vocab=512, max_len=8, num_layers=L, image_size=S, lanes=17)        # the handle holds at most 16 lanes
