@@ -81,7 +81,7 @@ def test_c_host_binds_the_library_without_python(built_lib, tmp_path):
 def test_library_has_blackwell_code(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "sm_100" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):           # tcgen05.mma, TMA load, tcgen05.ld
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):   # tcgen05.mma, TMA load, TMA store, tcgen05.ld
         assert mnemonic in sass, "expected %s in the SASS of libfpnmt.so" % mnemonic
     # legacy mma.sync (HMMA) is allowed only where a dimension of the product is 16 (the 16 baseline queries / 16 memory
     # tokens), below tcgen05's minimum M of 64: the encoder's flash attention and the once-per-batch cross-attention operand
@@ -284,3 +284,17 @@ def test_bench_reference_arm_line_shape():
     assert bench.WORKLOADS["c2"]["backbone"] == "resnet50" and bench.WORKLOADS["c2"]["batch"] == 64
     p = bench.measured_peaks()
     assert p["hbm_gbs"] > 1000 and p["tf"] > 100
+
+
+def test_python_mirror_of_the_config_struct_and_option_bits_matches_the_header():
+    """fpnmt/_lib.py restates `fpnmt_config` (ctypes) and the FPNMT_OPT_* bits by hand; a drift would silently select other kernels
+    or shift every field.  Field names / order and every option bit are compared with include/fpnmt.h."""
+    import re
+    from fpnmt import _lib
+    hdr = open(os.path.join(ROOT, "include", "fpnmt.h")).read()
+    body = hdr[hdr.index("typedef struct fpnmt_config {"):hdr.index("} fpnmt_config;")]
+    fields = re.findall(r"^\s*(?:int32_t|float)\s+(\w+)(?:\[\d+\])?;", body, flags=re.M)
+    assert fields == [n for n, _ in _lib.FpnmtConfig._fields_], (fields, [n for n, _ in _lib.FpnmtConfig._fields_])
+    bits = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"FPNMT_OPT_(\w+)\s*=\s*(\d+)", hdr)}
+    assert bits == _lib.OPT_BITS, (sorted(bits.items()), sorted(_lib.OPT_BITS.items()))
+    assert len(set(bits.values())) == len(bits) and all(v & (v - 1) == 0 for v in bits.values())      # distinct single bits
